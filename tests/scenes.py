@@ -1,0 +1,34 @@
+"""Seeded scene/model configurations shared by the golden generator and tests."""
+
+import torch
+
+from dynibar_b200 import synthetic
+
+# name -> config.  Small enough that the reference finishes in seconds on CPU.
+GOLDEN_CONFIGS = {
+    # render_rays_mv: coarse + fine, 7 dynamic + 5 static views, masks stressed
+    "mv_small": dict(mono=False, H=48, W=64, V_dy=7, V_st=5, rays=40,
+                     N_samples=16, N_importance=16, num_vv=0, inv_uniform=True,
+                     anti_alias_pooling=1, mask_rgb=0, seed=11, stress=True),
+    # same path, linear-depth sampling, no anti-alias pooling, mask_rgb on
+    "mv_linear": dict(mono=False, H=40, W=56, V_dy=7, V_st=4, rays=24,
+                      N_samples=20, N_importance=12, num_vv=0, inv_uniform=False,
+                      anti_alias_pooling=0, mask_rgb=1, seed=12, stress=False),
+    # render_rays_mono (BASELINE config 1 shape scaled): 32 samples,
+    # 6 temporal + 2 virtual dynamic views, 4 static views, shift=5
+    "mono_small": dict(mono=True, H=36, W=64, V_dy=8, V_st=4, rays=24,
+                       N_samples=32, N_importance=0, num_vv=2, inv_uniform=True,
+                       anti_alias_pooling=1, mask_rgb=1, seed=13, stress=True),
+}
+
+
+def build(cfg, sigma_bias=-4.0):
+  batch, feat_c, feat_f, frame, t, offs = synthetic.make_scene(
+      H=cfg["H"], W=cfg["W"], V_dy=cfg["V_dy"], V_st=cfg["V_st"],
+      num_vv=cfg["num_vv"], seed=cfg["seed"], rays=cfg["rays"],
+      stress=cfg.get("stress", False))
+  args = synthetic.make_args(cfg["anti_alias_pooling"], cfg["mask_rgb"])
+  model, args = synthetic.make_model(cfg["N_samples"], cfg["N_importance"],
+                                     args=args, seed=cfg["seed"],
+                                     mono=cfg["mono"], sigma_bias=sigma_bias)
+  return batch, feat_c, feat_f, frame, t, offs, model, args
