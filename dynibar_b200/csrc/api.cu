@@ -1,0 +1,157 @@
+// C ABI glue: error reporting, network handles, precision dispatch.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "nets.cuh"
+
+namespace dyn {
+
+unsigned long long g_launches = 0;
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+}  // namespace dyn
+
+using namespace dyn;
+
+extern "C" {
+
+int dyn_version(void) { return 100; }
+
+unsigned long long dyn_launch_count(int reset) {
+  unsigned long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+const char* dyn_last_error(void) { return err_buf(); }
+
+int dyn_device_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return n;
+}
+
+size_t dyn_net_param_count(int kind) {
+  switch (kind) {
+    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().total;
+    case DYN_NET_STATIC: return (size_t)static_layout(true).total;  // with `s`; without = count - 1
+    case DYN_NET_MOTION: return (size_t)motion_layout(6).total;
+    default: return 0;
+  }
+}
+
+size_t dyn_net_packed_bytes(int kind) {
+  (void)kind;
+  return 0;  // tensor-core operand images: see nets_tc.cu (filled in when that path is linked)
+}
+
+int dyn_net_create(int kind, const float* params, size_t n_params, void* packed, int n_samples,
+                   float shift, int anti_alias_pooling, int mask_rgb, void* stream, dyn_net_t* out) {
+  (void)stream;
+  DYN_CHECK_ARG(out != nullptr && params != nullptr);
+  dyn_net* n = (dyn_net*)calloc(1, sizeof(dyn_net));
+  if (!n) return fail(DYN_E_INVALID, "out of host memory");
+  n->kind = kind;
+  n->params = params;
+  n->packed = packed;
+  n->n_samples = n_samples;
+  n->shift = shift;
+  n->anti_alias = anti_alias_pooling;
+  n->mask_rgb = mask_rgb;
+  size_t expect = 0;
+  if (kind == DYN_NET_DYNAMIC) {
+    n->dl = dynamic_layout();
+    expect = n->dl.total;
+  } else if (kind == DYN_NET_STATIC) {
+    n->sl = static_layout(anti_alias_pooling != 0);
+    expect = n->sl.total;
+  } else if (kind == DYN_NET_MOTION) {
+    // coeff_linear is [3*nb, 256] + [3*nb]: solve nb from the count
+    size_t fixed = (size_t)motion_layout(1).total - (3 * 256 + 3);
+    size_t rest = n_params - fixed;
+    if (n_params <= fixed || rest % (3 * 257) != 0) {
+      free(n);
+      return fail(DYN_E_INVALID, "MotionMLP: unexpected parameter count %zu", n_params);
+    }
+    n->nb = (int)(rest / (3 * 257));
+    if (n->nb < 1 || n->nb > 8) {
+      free(n);
+      return fail(DYN_E_INVALID, "MotionMLP: num_basis %d unsupported (1..8)", n->nb);
+    }
+    n->ml = motion_layout(n->nb);
+    expect = n->ml.total;
+  } else {
+    free(n);
+    return fail(DYN_E_INVALID, "unknown net kind %d", kind);
+  }
+  if (expect != n_params) {
+    free(n);
+    return fail(DYN_E_INVALID, "net kind %d: got %zu parameters, expected %zu", kind, n_params, expect);
+  }
+  *out = n;
+  return DYN_OK;
+}
+
+void dyn_net_destroy(dyn_net_t net) { free(net); }
+
+size_t dyn_motion_workspace_bytes(int R, int S) { return motion_f32_workspace((long long)R * S); }
+
+size_t dyn_net_workspace_bytes(int kind, int R, int S, int V) {
+  if (kind == DYN_NET_DYNAMIC) return net_dynamic_f32_workspace(R, S, V);
+  if (kind == DYN_NET_STATIC) return net_static_f32_workspace(R, S, V);
+  if (kind == DYN_NET_MOTION) return motion_f32_workspace((long long)R * S);
+  return 0;
+}
+
+int dyn_motion_coeffs(dyn_net_t motion, const float* pts, float time, int R, int S, float* coeff,
+                      void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  DYN_CHECK_ARG(motion && motion->kind == DYN_NET_MOTION && pts && coeff && workspace);
+  DYN_CHECK_ARG(R >= 0 && S >= 1);
+  if (precision != DYN_PREC_FP32) return fail(DYN_E_INVALID, "precision %d not built", precision);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = motion_f32(motion, pts, 3, false, time, (long long)R * S, coeff, workspace, workspace_bytes, st);
+  if (rc) return rc;
+  return zero_last_samples(coeff, R, S, 3 * motion->nb, st);
+}
+
+int dyn_motion_mlp(dyn_net_t motion, const float* xyzt, int N, float* coeff, void* workspace,
+                   size_t workspace_bytes, int precision, void* stream) {
+  DYN_CHECK_ARG(motion && motion->kind == DYN_NET_MOTION && xyzt && coeff && workspace && N >= 0);
+  if (precision != DYN_PREC_FP32) return fail(DYN_E_INVALID, "precision %d not built", precision);
+  return motion_f32(motion, xyzt, 4, true, 0.f, N, coeff, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dyn_net_dynamic(dyn_net_t net, const float* pts, const float* rgb_feat, const float* ray_dir,
+                    const float* mask, float time, int R, int S, int V, float* raw, void* workspace,
+                    size_t workspace_bytes, int precision, void* stream) {
+  DYN_CHECK_ARG(net && net->kind == DYN_NET_DYNAMIC && pts && rgb_feat && ray_dir && mask && raw);
+  DYN_CHECK_ARG(workspace && R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
+  if (precision != DYN_PREC_FP32) return fail(DYN_E_INVALID, "precision %d not built", precision);
+  return net_dynamic_f32(net, pts, rgb_feat, ray_dir, mask, time, R, S, V, raw, workspace,
+                         workspace_bytes, (cudaStream_t)stream);
+}
+
+int dyn_net_static(dyn_net_t net, const float* pts, const float* ref_rays, const float* src_rays,
+                   const float* rgb_feat, const float* ray_diff, const float* mask, int R, int S, int V,
+                   float* raw, void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  DYN_CHECK_ARG(net && net->kind == DYN_NET_STATIC && pts && ref_rays && src_rays && rgb_feat);
+  DYN_CHECK_ARG(ray_diff && mask && raw && workspace && R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
+  if (precision != DYN_PREC_FP32) return fail(DYN_E_INVALID, "precision %d not built", precision);
+  return net_static_f32(net, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask, R, S, V, raw, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

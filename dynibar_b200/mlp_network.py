@@ -26,24 +26,9 @@ def _seq(*dims_and_acts):
 
 
 class _PackedNet(nn.Module):
-  """Base: caches a flat fp32 parameter blob for the C-ABI and re-packs when
-  any parameter's `_version` changes (training updates)."""
+  """Base class of the containers (packing/caching lives in weights.py)."""
 
   kind = None  # 'dynamic' | 'static' | 'motion'
-
-  def __init__(self):
-    super().__init__()
-    self._pack_cache = None
-
-  def param_versions(self):
-    return tuple((p.data_ptr(), p._version) for p in self.parameters())
-
-  def packed(self, device):
-    from dynibar_b200 import weights as _w
-    key = (self.param_versions(), str(device))
-    if self._pack_cache is None or self._pack_cache[0] != key:
-      self._pack_cache = (key, _w.pack(self, device))
-    return self._pack_cache[1]
 
 
 class DynibarDynamic(_PackedNet):

@@ -1,0 +1,376 @@
+"""Per-ray renderer: drop-in for ibrnet/render_ray.py on the CUDA library.
+
+Public surface (same names / signatures / returned dict keys as the
+reference): `render_rays_mv` (render_ray.py:600), `render_rays_mono` (:870),
+`sample_along_camera_ray` (:67), `raw2outputs` (:214), `raw2outputs_vanilla`
+(:134), `compute_optical_flow` (:333), `compute_ref_plucker_coordinate` (:372),
+`compute_src_plucker_coordinate` (:380), `z_to_s` (:399).
+
+All math runs in `csrc/` kernels through the C ABI (include/dynibar_b200.h);
+this file only allocates tensors and sequences calls.  Inference only: the
+kernels have no backward yet, so `requires_grad` inputs raise.
+"""
+
+from collections import OrderedDict
+import ctypes as C
+
+import torch
+
+from dynibar_b200 import _lib
+from dynibar_b200 import weights as _weights
+from dynibar_b200._lib import lib, ptr, f32c, check, stream, dev_of
+from dynibar_b200.projection import project_gather
+
+# GEMM precision of the network kernels: _lib.PREC_FP32 (SIMT parity mode) or
+# _lib.PREC_BF16 (tcgen05, bf16 operands / fp32 accumulate).
+PRECISION = _lib.PREC_FP32
+
+
+def set_precision(name):
+  global PRECISION
+  PRECISION = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[name]
+
+
+def _no_grad_only(*tensors):
+  if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+    raise NotImplementedError(
+        "dynibar_b200 kernels are forward-only (training backward = SURVEY 8(f) f2); "
+        "call under torch.no_grad() with detached inputs")
+
+
+def _scalar(x):
+  return float(x.reshape(-1)[0]) if torch.is_tensor(x) else float(x)
+
+
+# ---------------------------------------------------------------------------
+# a2
+# ---------------------------------------------------------------------------
+def sample_along_camera_ray(ray_o, ray_d, depth_range, N_samples, inv_uniform=False, det=False,
+                            jitter=None):
+  """render_ray.py:67-131.  `jitter` ([R,N_samples] U[0,1)) lets a caller
+  supply the random draws; with det=False and jitter=None they are drawn with
+  torch.rand like the reference (:119)."""
+  R = ray_o.shape[0]
+  dev = dev_of(ray_o)
+  near, far = _scalar(depth_range[0, 0]), _scalar(depth_range[0, 1])
+  assert near > 0 and far > 0 and far > near
+  if not det and jitter is None:
+    jitter = torch.rand(R, N_samples, device=dev)
+  if det:
+    jitter = None
+  pts = torch.empty(R, N_samples, 3, device=dev)
+  z = torch.empty(R, N_samples, device=dev)
+  s = torch.empty(R, N_samples, device=dev)
+  with torch.cuda.device(dev):
+    check(lib.dyn_sample_rays(ptr(f32c(ray_o)), ptr(f32c(ray_d)), near, far, R, N_samples,
+                              int(bool(inv_uniform)),
+                              ptr(f32c(jitter)) if jitter is not None else None,
+                              ptr(pts), ptr(z), ptr(s), stream()))
+  return pts, z, s
+
+
+def z_to_s(z_vals, near_depth_value, far_depth_value):
+  """render_ray.py:399-404 (elementwise; kept in torch, it is not on the hot
+  path -- the kernels emit s_vals directly)."""
+  return ((1.0 / z_vals) - (1.0 / near_depth_value)) / (1.0 / far_depth_value - 1.0 / near_depth_value)
+
+
+def points_from_depths(ray_o, ray_d, z_vals, depth_range):
+  R, S = z_vals.shape
+  dev = dev_of(z_vals)
+  near, far = _scalar(depth_range[0, 0]), _scalar(depth_range[0, 1])
+  pts = torch.empty(R, S, 3, device=dev)
+  s = torch.empty(R, S, device=dev)
+  with torch.cuda.device(dev):
+    check(lib.dyn_points_from_depths(ptr(f32c(ray_o)), ptr(f32c(ray_d)), ptr(f32c(z_vals)), near,
+                                     far, R, S, ptr(pts), ptr(s), stream()))
+  return pts, s
+
+
+# ---------------------------------------------------------------------------
+# a3
+# ---------------------------------------------------------------------------
+def motion_mlp_forward(module, xyzt):
+  """MotionMLP.forward on [...,4] rows (mlp_network.py:605-618)."""
+  _no_grad_only(xyzt)
+  dev = dev_of(xyzt)
+  net = _weights.packed_of(module, dev)
+  x = f32c(xyzt).reshape(-1, 4)
+  N = x.shape[0]
+  out = torch.empty(N, 3 * net.num_basis, device=dev)
+  nbytes = lib.dyn_motion_workspace_bytes(N, 1)
+  ws = _lib.workspace.get(nbytes, dev)
+  with torch.cuda.device(dev):
+    check(lib.dyn_motion_mlp(net.handle, ptr(x), N, ptr(out), ws.data_ptr(), nbytes, PRECISION,
+                             stream()))
+  div = float(getattr(_weights.de_parallel(module), "sf_mag_div", 1.0))
+  if div != 1.0:
+    out = out / div
+  return out.reshape(xyzt.shape[:-1] + (out.shape[-1],))
+
+
+def motion_coefficients(module, pts, t):
+  """coeffs [R,S,3*nb], last round(0.1*S) samples zeroed (render_ray.py:459-472)."""
+  dev = dev_of(pts)
+  net = _weights.packed_of(module, dev)
+  R, S = pts.shape[:2]
+  out = torch.empty(R, S, 3 * net.num_basis, device=dev)
+  nbytes = lib.dyn_motion_workspace_bytes(R, S)
+  ws = _lib.workspace.get(nbytes, dev)
+  with torch.cuda.device(dev):
+    check(lib.dyn_motion_coeffs(net.handle, ptr(f32c(pts)), float(t), R, S, ptr(out),
+                                ws.data_ptr(), nbytes, PRECISION, stream()))
+  return out
+
+
+def displaced_points(pts, coeff, basis, frame_idx, offsets, num_vv=0):
+  """pts_3d_seq [len(offsets)+num_vv, R, S, 3] (render_ray.py:479-497, :988-991)."""
+  dev = dev_of(pts)
+  R, S = pts.shape[:2]
+  n_off = len(offsets)
+  T, nb = basis.shape
+  seq = torch.empty(n_off + num_vv, R, S, 3, device=dev)
+  offs = (C.c_int * max(n_off, 1))(*[int(o) for o in offsets])
+  with torch.cuda.device(dev):
+    check(lib.dyn_traj_displace(ptr(f32c(pts)), ptr(f32c(coeff)), ptr(f32c(basis).to(dev)), T, nb,
+                                int(frame_idx), offs, n_off, int(num_vv), R, S, ptr(seq), stream()))
+  return seq
+
+
+# ---------------------------------------------------------------------------
+# a7
+# ---------------------------------------------------------------------------
+def compute_ref_plucker_coordinate(ray_o, ray_d):
+  R = ray_o.shape[0]
+  out = torch.empty(R, 6, device=dev_of(ray_o))
+  with torch.cuda.device(ray_o.device):
+    check(lib.dyn_plucker_ref(ptr(f32c(ray_o)), ptr(f32c(ray_d)), R, ptr(out), stream()))
+  return out
+
+
+def compute_src_plucker_coordinate(pts, src_cameras):
+  """pts [R,S,3], src_cameras [1,V,34] -> [R,S,V,6] (render_ray.py:380-396)."""
+  R, S = pts.shape[:2]
+  V = src_cameras.shape[1]
+  out = torch.empty(R, S, V, 6, device=dev_of(pts))
+  with torch.cuda.device(pts.device):
+    check(lib.dyn_plucker_src(ptr(f32c(pts)), ptr(f32c(src_cameras)), V, R, S, ptr(out), stream()))
+  return out
+
+
+# ---------------------------------------------------------------------------
+# a8-a11
+# ---------------------------------------------------------------------------
+def net_dynamic_forward(module, pts, rgb_feat, ray_dir, mask, time):
+  """DynibarDynamic.forward (mlp_network.py:236-316).  `time` is the
+  reference's [R,S,1] tensor (constant) or a scalar."""
+  _no_grad_only(pts, rgb_feat)
+  dev = dev_of(pts)
+  net = _weights.packed_of(module, dev)
+  R, S, V = rgb_feat.shape[:3]
+  raw = torch.empty(R, S, 4, device=dev)
+  nbytes = lib.dyn_net_workspace_bytes(_lib.NET_DYNAMIC, R, S, V)
+  ws = _lib.workspace.get(nbytes, dev)
+  t = _scalar(time.float() if torch.is_tensor(time) else time)
+  with torch.cuda.device(dev):
+    check(lib.dyn_net_dynamic(net.handle, ptr(f32c(pts)), ptr(f32c(rgb_feat)), ptr(f32c(ray_dir)),
+                              ptr(f32c(mask)), t, R, S, V, ptr(raw), ws.data_ptr(), nbytes,
+                              PRECISION, stream()))
+  return raw
+
+
+def net_static_forward(module, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask):
+  """DynibarStatic.forward (mlp_network.py:423-527)."""
+  _no_grad_only(pts, rgb_feat)
+  dev = dev_of(pts)
+  net = _weights.packed_of(module, dev)
+  R, S, V = rgb_feat.shape[:3]
+  raw = torch.empty(R, S, 4, device=dev)
+  nbytes = lib.dyn_net_workspace_bytes(_lib.NET_STATIC, R, S, V)
+  ws = _lib.workspace.get(nbytes, dev)
+  with torch.cuda.device(dev):
+    check(lib.dyn_net_static(net.handle, ptr(f32c(pts)), ptr(f32c(ref_rays)), ptr(f32c(src_rays)),
+                             ptr(f32c(rgb_feat)), ptr(f32c(ray_diff)), ptr(f32c(mask)), R, S, V,
+                             ptr(raw), ws.data_ptr(), nbytes, PRECISION, stream()))
+  return raw
+
+
+# ---------------------------------------------------------------------------
+# a12
+# ---------------------------------------------------------------------------
+def _composite(raw_dy, raw_st, z, mask_dy, V_dy, min_dy, mask_st, V_st, min_st):
+  R, S = z.shape
+  dev = dev_of(z)
+  rays = torch.empty(R, 11, device=dev)
+  samp = torch.empty(5, R, S, device=dev)
+  with torch.cuda.device(dev):
+    check(lib.dyn_composite(ptr(f32c(raw_dy)), ptr(f32c(raw_st)), ptr(f32c(z)), ptr(f32c(mask_dy)),
+                            V_dy, min_dy, ptr(f32c(mask_st)), V_st, min_st, R, S, ptr(rays),
+                            ptr(samp), stream()))
+  return OrderedDict([
+      ("rgb", rays[:, 0:3]), ("rgb_static", rays[:, 3:6]), ("rgb_dy", rays[:, 6:9]),
+      ("depth", rays[:, 9]), ("alpha_dy", samp[0]), ("weights_dy", samp[1]),
+      ("weights_st", samp[2]), ("alpha", samp[3]), ("weights", samp[4]),
+      ("mask", rays[:, 10] > 0.5), ("z_vals", z),
+  ])
+
+
+def _composite_vanilla(raw, z, mask, V, min_views):
+  R, S = z.shape
+  dev = dev_of(z)
+  rays = torch.empty(R, 5, device=dev)
+  samp = torch.empty(2, R, S, device=dev)
+  with torch.cuda.device(dev):
+    check(lib.dyn_composite_vanilla(ptr(f32c(raw)), ptr(f32c(z)), ptr(f32c(mask)), V, min_views,
+                                    R, S, ptr(rays), ptr(samp), stream()))
+  return OrderedDict([
+      ("rgb", rays[:, 0:3]), ("depth", rays[:, 3]), ("weights", samp[0]),
+      ("mask", rays[:, 4] > 0.5), ("alpha", samp[1]), ("z_vals", z),
+  ])
+
+
+def raw2outputs(raw_dy, raw_static, z_vals, mask_dy, mask_static, raw_noise_std=0.0):
+  """render_ray.py:214-330; mask_* are the per-sample [R,S] validity masks."""
+  return _composite(raw_dy, raw_static, z_vals, mask_dy.float(), 1, 0, mask_static.float(), 1, 0)
+
+
+def raw2outputs_vanilla(raw, z_vals, mask):
+  """render_ray.py:134-211."""
+  return _composite_vanilla(raw, z_vals, mask.float(), 1, 0)
+
+
+# ---------------------------------------------------------------------------
+# a13
+# ---------------------------------------------------------------------------
+def resample_depths(z_vals, weights, N_importance, inv_uniform, det=True, u=None):
+  """sample_pdf on the interior weights + concat + sort
+  (render_ray.py:790-819) -> [R, S+N_importance] ascending depths."""
+  R, S = z_vals.shape
+  dev = dev_of(z_vals)
+  if not det and u is None:
+    u = torch.rand(R, N_importance, device=dev)
+  if det:
+    u = None
+  out = torch.empty(R, S + N_importance, device=dev)
+  with torch.cuda.device(dev):
+    check(lib.dyn_resample(ptr(f32c(z_vals)), ptr(f32c(weights)),
+                           ptr(f32c(u)) if u is not None else None, R, S, N_importance,
+                           int(bool(inv_uniform)), ptr(out), stream()))
+  return out
+
+
+# ---------------------------------------------------------------------------
+# a14
+# ---------------------------------------------------------------------------
+def _flow_sceneflow(weights, pts_seq, src_cameras, uv, coeff, basis, frame_idx, sf_k, n_flow):
+  R, S = weights.shape
+  dev = dev_of(weights)
+  flows = torch.empty(n_flow, R, 2, device=dev)
+  exp_sf = torch.empty(R, 3, device=dev) if coeff is not None else None
+  T, nb = (basis.shape if basis is not None else (0, 1))
+  with torch.cuda.device(dev):
+    check(lib.dyn_flow_sceneflow(
+        ptr(f32c(weights)), ptr(f32c(pts_seq)), ptr(f32c(src_cameras)), ptr(f32c(uv)),
+        ptr(f32c(coeff)) if coeff is not None else None,
+        ptr(f32c(basis).to(dev)) if basis is not None else None, T, nb, int(frame_idx), int(sf_k),
+        int(n_flow), R, S, ptr(flows), ptr(exp_sf) if exp_sf is not None else None, stream()))
+  return flows, exp_sf
+
+
+def compute_optical_flow(outputs_coarse, raw_pts_3d_seq, src_cameras, uv_grid):
+  """render_ray.py:333-358 -> [V,R,2]."""
+  V = raw_pts_3d_seq.shape[0]
+  flows, _ = _flow_sceneflow(outputs_coarse["weights"], raw_pts_3d_seq, src_cameras[:, :V],
+                             uv_grid, None, None, 0, 0, V)
+  return flows
+
+
+# ---------------------------------------------------------------------------
+# a15 orchestrators
+# ---------------------------------------------------------------------------
+
+def _render_pass(ray_batch, feat_dy, feat_st, pts, z, s, t, frame_idx, offsets, num_vv, net_dy,
+                 net_st, motion, basis, flow_views, sf_k, want_extras=True, want_vanilla_st=False):
+  """One coarse-or-fine evaluation at the reference time
+  (render_ray.py:455-597 == :672-782 == :951-1096)."""
+  cam, ray_o, ray_d = ray_batch["camera"], ray_batch["ray_o"], ray_batch["ray_d"]
+  ref_plucker = compute_ref_plucker_coordinate(ray_o, ray_d)  # [d_hat, o x d_hat]
+  ray_dir = ref_plucker[:, :3]  # == F.normalize(ray_d) (render_ray.py:455)
+  coeff = motion_coefficients(motion, pts, t)
+  seq = displaced_points(pts, coeff, basis, frame_idx, offsets, num_vv)
+  f_dy, _, m_dy = project_gather(pts, seq, cam, ray_batch["src_rgbs"], ray_batch["src_cameras"],
+                                 feat_dy)
+  f_st, rd_st, m_st = project_gather(pts, None, cam, ray_batch["static_src_rgbs"],
+                                     ray_batch["static_src_cameras"], feat_st)
+  raw_dy = net_dynamic_forward(net_dy, pts, f_dy, ray_dir, m_dy, t)
+  raw_st = net_static_forward(net_st, pts, ref_plucker,
+                              compute_src_plucker_coordinate(pts, ray_batch["static_src_cameras"]),
+                              f_st, rd_st, m_st)
+  V_dy, V_st = m_dy.shape[2], m_st.shape[2]
+  # a sample counts when MORE THAN ONE view sees it (render_ray.py:524-529)
+  out = _composite(raw_dy, raw_st, z, m_dy, V_dy, 1, m_st, V_st, 1)
+  out_dy = _composite_vanilla(raw_dy, z, m_dy, V_dy, 1)
+  out_st = _composite_vanilla(raw_st, z, m_st, V_st, 1) if want_vanilla_st else None
+  if want_extras:
+    nflow = seq.shape[0] if flow_views is None else flow_views
+    flows, exp_sf = _flow_sceneflow(out["weights"], seq, ray_batch["src_cameras"],
+                                    ray_batch["uv_grid"], coeff, basis, frame_idx, sf_k, nflow)
+    out["render_flows"] = flows
+    out["s_vals"] = s
+    out["exp_sf"] = exp_sf
+  return out, out_dy, out_st
+
+
+def render_rays_mv(frame_idx, time_embedding, time_offset, ray_batch, model, projector,
+                   coarse_featmaps, fine_featmaps, N_samples, args, inv_uniform=False,
+                   N_importance=0, raw_noise_std=0.0, det=False, white_bkgd=False, is_train=True,
+                   jitter=None, u=None):
+  """Coarse + fine rendering for the Nvidia multi-view benchmark
+  (render_ray.py:600-867).  Extra keyword-only inputs `jitter` / `u` carry the
+  random draws of :119 / :34 when det=False (drawn with torch.rand if None).
+  Returns the reference's dict: outputs_coarse_ref, outputs_fine_ref,
+  outputs_fine_ref_dy, outputs_fine_anchor(None), outputs_fine_anchor_dy(None)."""
+  assert N_importance > 0  # render_ray.py:787
+  with torch.no_grad():
+    t = _scalar(time_embedding[0].float())
+    offs = [int(o) for o in time_offset[0]]
+    fidx = int(frame_idx[0])
+    ret = {"outputs_coarse": None, "outputs_fine": None}
+    pts, z, _ = sample_along_camera_ray(ray_batch["ray_o"], ray_batch["ray_d"],
+                                        ray_batch["depth_range"], N_samples, inv_uniform, det, jitter)
+    out_c, _, _ = _render_pass(ray_batch, coarse_featmaps[0], coarse_featmaps[2], pts, z, None, t,
+                               fidx, offs, 0, model.net_coarse_dy, model.net_coarse_st,
+                               model.motion_mlp, model.trajectory_basis, None, 2, want_extras=False)
+    ret["outputs_coarse_ref"] = out_c
+    zf = resample_depths(z, out_c["weights"], N_importance, inv_uniform, det, u)
+    pts_f, s = points_from_depths(ray_batch["ray_o"], ray_batch["ray_d"], zf,
+                                  ray_batch["depth_range"])
+    out_f, out_f_dy, _ = _render_pass(ray_batch, fine_featmaps[0], fine_featmaps[2], pts_f, zf, s,
+                                      t, fidx, offs, 0, model.net_fine_dy, model.net_fine_st,
+                                      model.motion_mlp_fine, model.trajectory_basis_fine, None, 2)
+    ret["outputs_fine_ref"] = out_f
+    ret["outputs_fine_ref_dy"] = out_f_dy
+    ret["outputs_fine_anchor"] = None
+    ret["outputs_fine_anchor_dy"] = None
+  return ret
+
+
+def render_rays_mono(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, projector,
+                     N_samples, args, inv_uniform=False, N_importance=0, raw_noise_std=0.0,
+                     det=False, white_bkgd=False, is_train=True, num_vv=2, jitter=None):
+  """Coarse-only rendering for monocular video (render_ray.py:870-1277).
+  The training-only cross-time branch (:1099-1270) needs
+  autograd through the kernels and is not built yet."""
+  if is_train:
+    raise NotImplementedError("render_rays_mono(is_train=True): cross-time training branch "
+                              "(render_ray.py:1099-1270) is scheduled after the forward path")
+  with torch.no_grad():
+    t = _scalar(time_embedding[0].float())
+    pts, z, s = sample_along_camera_ray(ray_batch["ray_o"], ray_batch["ray_d"],
+                                        ray_batch["depth_range"], N_samples, inv_uniform, det, jitter)
+    out, out_dy, out_st = _render_pass(ray_batch, featmaps[0], featmaps[2], pts, z, s, t,
+                                       int(frame_idx[0]), [int(o) for o in time_offset[0]], num_vv,
+                                       model.net_coarse_dy, model.net_coarse_st, model.motion_mlp,
+                                       model.trajectory_basis, 6, 1, want_vanilla_st=True)
+  return {"outputs_coarse": None, "outputs_fine": None, "outputs_coarse_ref": out,
+          "outputs_coarse_ref_dy": out_dy, "outputs_coarse_st": out_st}

@@ -1,0 +1,182 @@
+/* dynibar_b200 -- C ABI of the B200-native DynIBaR per-ray IBR hot path.
+ *
+ * The reference (google/dynibar @ 5412b55) has no FFI layer: its boundary for
+ * this path is the Python call surface of ibrnet/render_ray.py,
+ * ibrnet/projection.py and ibrnet/mlp_network.py.  Each entry point below
+ * names the reference function (file:line under /root/reference) it replaces;
+ * `dynibar_b200/*.py` binds them with ctypes behind the reference's own
+ * function / class names.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *     tensors are dense row-major fp32 unless stated; shapes in comments.
+ *   - the caller owns every buffer (inputs, outputs, workspace, packed
+ *     weights); the library never allocates or frees device memory and keeps
+ *     no device pointer after return except inside a `dyn_net_t` handle.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it,
+ *     nothing synchronises.
+ *   - return 0 on success, a negative DYN_E_* otherwise; `dyn_last_error()`
+ *     returns a thread-local message.  No C++ exceptions cross the ABI.
+ *   - R rays, S samples per ray, V source views, C feature channels (32),
+ *     F = C + 3.
+ */
+#ifndef DYNIBAR_B200_H_
+#define DYNIBAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYN_OK 0
+#define DYN_E_INVALID -1 /* bad argument / unsupported shape */
+#define DYN_E_CUDA -2    /* a CUDA runtime call or launch failed */
+#define DYN_E_WORKSPACE -3 /* workspace too small */
+
+#define DYN_NET_DYNAMIC 0 /* DynibarDynamic, mlp_network.py:129 */
+#define DYN_NET_STATIC 1  /* DynibarStatic,  mlp_network.py:319 */
+#define DYN_NET_MOTION 2  /* MotionMLP,      mlp_network.py:558 */
+
+#define DYN_PREC_FP32 0 /* SIMT fp32 everywhere (parity mode) */
+#define DYN_PREC_BF16 1 /* tcgen05: bf16 operands, fp32 accumulate/statistics */
+
+typedef struct dyn_net* dyn_net_t;
+
+int dyn_version(void);
+const char* dyn_last_error(void);
+/* Number of SMs etc. of the current device (for grid sizing diagnostics). */
+int dyn_device_sm_count(void);
+/* Kernels launched by this library since load (or the last reset). */
+unsigned long long dyn_launch_count(int reset);
+
+/* ---- weights ------------------------------------------------------------
+ * `params` is the flat fp32 concatenation of the network's state_dict tensors
+ * in the canonical order documented in dynibar_b200/weights.py (reference key
+ * names, mlp_network.py:159-214 / :349-403 / :591-603).  `n_params` is checked
+ * against the expected count.  `packed` is a caller-owned device buffer of
+ * dyn_net_packed_bytes(kind) bytes that receives the tensor-core operand
+ * images (bf16, UMMA canonical layout); it may be NULL for DYN_PREC_FP32 use.
+ * n_samples sizes the sinusoid table of the dynamic net (mlp_network.py:218).
+ */
+size_t dyn_net_param_count(int kind);
+size_t dyn_net_packed_bytes(int kind);
+int dyn_net_create(int kind, const float* params, size_t n_params, void* packed,
+                   int n_samples, float shift, int anti_alias_pooling,
+                   int mask_rgb, void* stream, dyn_net_t* out);
+void dyn_net_destroy(dyn_net_t net);
+
+/* ---- a2: sample_along_camera_ray, render_ray.py:67-131 -------------------
+ * ray_o, ray_d [R,3]; jitter [R,S] of U[0,1) or NULL (det=True).
+ * Outputs pts [R,S,3], z_vals [R,S], s_vals [R,S]. */
+int dyn_sample_rays(const float* ray_o, const float* ray_d, float near_depth,
+                    float far_depth, int R, int S, int inv_uniform,
+                    const float* jitter, float* pts, float* z_vals,
+                    float* s_vals, void* stream);
+
+/* pts = z * d + o and s = z_to_s(z) for given depths
+ * (render_ray.py:822-831, :399-404).  s_vals may be NULL. */
+int dyn_points_from_depths(const float* ray_o, const float* ray_d,
+                           const float* z_vals, float near_depth,
+                           float far_depth, int R, int S, float* pts,
+                           float* s_vals, void* stream);
+
+/* ---- a3: MotionMLP + trajectory displacement ------------------------------
+ * mlp_network.py:605-618; render_ray.py:361-369, :462-500.
+ * coeff [R,S,3*nb] with the last round(0.1*S) samples zeroed. */
+size_t dyn_motion_workspace_bytes(int R, int S);
+int dyn_motion_coeffs(dyn_net_t motion, const float* pts, float time, int R,
+                      int S, float* coeff, void* workspace,
+                      size_t workspace_bytes, int precision, void* stream);
+/* generic MotionMLP forward on xyzt rows [N,4] -> [N,3*nb]
+ * (MotionMLP.forward, no zeroing). */
+int dyn_motion_mlp(dyn_net_t motion, const float* xyzt, int N, float* coeff,
+                   void* workspace, size_t workspace_bytes, int precision,
+                   void* stream);
+/* pts_seq[v] = pts + traj(frame+off_v) - traj(frame) for the n_off temporal
+ * offsets, followed by num_vv copies of pts.  basis [T,nb] (model.py:18-30).
+ * offsets_host is a HOST array.  pts_seq [n_off+num_vv, R, S, 3]. */
+int dyn_traj_displace(const float* pts, const float* coeff, const float* basis,
+                      int T, int nb, int frame_idx, const int* offsets_host,
+                      int n_off, int num_vv, int R, int S, float* pts_seq,
+                      void* stream);
+
+/* ---- a4-a6: Projector.compute_with_motions, projection.py:103-176 ---------
+ * xyz_st [R,S,3]; xyz [V,R,S,3] or NULL (every view uses xyz_st: the static
+ * branch, render_ray.py:498-500); query_cam [34]; src_rgbs [V,H,W,3]
+ * channels-last in [0,1]; src_cams [V,34]; featmaps [V,C,h,w] (reference
+ * layout).  Outputs rgb_feat [R,S,V,3+C], ray_diff [R,S,V,4], mask [R,S,V].
+ * feat_cl_ws: workspace of V*h*w*C floats for the channels-last copy of the
+ * feature maps. */
+int dyn_project_gather(const float* xyz_st, const float* xyz,
+                       const float* query_cam, const float* src_rgbs,
+                       const float* src_cams, const float* featmaps, int V,
+                       int R, int S, int H, int W, int C, int h, int w,
+                       float* feat_cl_ws, float* rgb_feat, float* ray_diff,
+                       float* mask, void* stream);
+/* compute_projections only (projection.py:32-59): pix [V,N,2], front [V,N] u8 */
+int dyn_compute_projections(const float* xyz, const float* src_cams, int V,
+                            int N, float* pix, uint8_t* front, void* stream);
+
+/* ---- a7: Plucker coordinates, render_ray.py:372-396 ---------------------- */
+int dyn_plucker_ref(const float* ray_o, const float* ray_d, int R, float* out6,
+                    void* stream);
+int dyn_plucker_src(const float* pts, const float* src_cams, int V, int R,
+                    int S, float* out /* [R,S,V,6] */, void* stream);
+
+/* ---- a8-a11: the two aggregation networks ---------------------------------
+ * DynibarDynamic.forward mlp_network.py:236-316 -> raw [R,S,4].
+ * ray_dir [R,3] is the NORMALISED target ray direction (render_ray.py:455). */
+size_t dyn_net_workspace_bytes(int kind, int R, int S, int V);
+int dyn_net_dynamic(dyn_net_t net, const float* pts, const float* rgb_feat,
+                    const float* ray_dir, const float* mask, float time, int R,
+                    int S, int V, float* raw, void* workspace,
+                    size_t workspace_bytes, int precision, void* stream);
+/* DynibarStatic.forward mlp_network.py:423-527 -> raw [R,S,4].
+ * ref_rays [R,6], src_rays [R,S,V,6] are the Plucker coordinates. */
+int dyn_net_static(dyn_net_t net, const float* pts, const float* ref_rays,
+                   const float* src_rays, const float* rgb_feat,
+                   const float* ray_diff, const float* mask, int R, int S,
+                   int V, float* raw, void* workspace, size_t workspace_bytes,
+                   int precision, void* stream);
+
+/* ---- a12: raw2outputs / raw2outputs_vanilla, render_ray.py:134-330 --------
+ * raw_* [R,S,4]; z_vals [R,S]; mask_* [R,S,V*] as produced by
+ * dyn_project_gather; a sample is "observed" when more than `min_views_*`
+ * views see it (1 for the reference-time pass render_ray.py:524-529, 0 for the
+ * anchor pass :1198-1200); ray mask = observed samples > 8.
+ * out_rays [R,11]: rgb(3) rgb_static(3) rgb_dy(3) depth(1) mask(1, 0/1);
+ * out_samples [5,R,S]: alpha_dy, weights_dy, weights_st, alpha, weights. */
+int dyn_composite(const float* raw_dy, const float* raw_st,
+                  const float* z_vals, const float* mask_dy, int V_dy,
+                  int min_views_dy, const float* mask_st, int V_st,
+                  int min_views_st, int R, int S, float* out_rays,
+                  float* out_samples, void* stream);
+/* out_rays [R,5]: rgb(3) depth(1) mask(1); out_samples [2,R,S]: weights, alpha */
+int dyn_composite_vanilla(const float* raw, const float* z_vals,
+                          const float* mask, int V, int min_views, int R,
+                          int S, float* out_rays, float* out_samples,
+                          void* stream);
+
+/* ---- a13: sample_pdf + merge, render_ray.py:19-64, :790-819 ---------------
+ * z_vals [R,S], weights [R,S] (coarse `weights`); u [R,Ni] uniforms or NULL
+ * (det: linspace(0,1,Ni)).  z_out [R,S+Ni] sorted ascending. */
+int dyn_resample(const float* z_vals, const float* weights, const float* u,
+                 int R, int S, int Ni, int inv_uniform, float* z_out,
+                 void* stream);
+
+/* ---- a14: flow / expected scene flow, render_ray.py:333-358, :585-595 -----
+ * weights [R,S]; pts_seq [V,R,S,3] (first n_flow views used); src_cams
+ * [V,34]; uv [R,2]; coeff [R,S,3*nb]; basis [T,nb]; sf_k = 2 (mv) or 1 (mono).
+ * flows [n_flow,R,2]; exp_sf [R,3]. */
+int dyn_flow_sceneflow(const float* weights, const float* pts_seq,
+                       const float* src_cams, const float* uv,
+                       const float* coeff, const float* basis, int T, int nb,
+                       int frame_idx, int sf_k, int n_flow, int R, int S,
+                       float* flows, float* exp_sf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNIBAR_B200_H_ */
