@@ -96,6 +96,27 @@ def f32c(t):
   return t.detach().to(torch.float32).contiguous()
 
 
+class Args(object):
+  """Marshals tensors for ONE library call and keeps every temporary
+  (contiguous / fp32 copies) alive until the caller drops this object, i.e.
+  until after the kernels have been enqueued.  Without this a temporary's
+  storage is returned to the caching allocator as soon as `ptr()` returns and
+  the next temporary overwrites it before the kernel reads it."""
+
+  def __init__(self):
+    self.keep = []
+
+  def __call__(self, t, dtype=torch.float32):
+    if t is None:
+      return None
+    c = t.detach()
+    if dtype == torch.float32:
+      c = c.to(torch.float32)
+    c = c.contiguous()
+    self.keep.append(c)
+    return ptr(c, dtype)
+
+
 def stream():
   return torch.cuda.current_stream().cuda_stream
 

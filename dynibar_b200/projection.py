@@ -5,7 +5,7 @@ projection + bilinear-gather kernel (csrc/geometry.cu).
 import torch
 
 from dynibar_b200 import _lib
-from dynibar_b200._lib import lib, ptr, f32c, check, stream, dev_of
+from dynibar_b200._lib import lib, ptr, f32c, check, stream, dev_of, Args
 
 
 class Projector(object):
@@ -32,8 +32,9 @@ class Projector(object):
     N = x.shape[1]
     pix = torch.empty(V, N, 2, device=x.device)
     front = torch.empty(V, N, dtype=torch.uint8, device=x.device)
+    A = Args()
     with torch.cuda.device(x.device):
-      check(lib.dyn_compute_projections(ptr(x), ptr(f32c(train_cameras)), V, N, ptr(pix),
+      check(lib.dyn_compute_projections(ptr(x), A(train_cameras), V, N, ptr(pix),
                                         ptr(front, torch.uint8), stream()))
     return pix.reshape(shape + (2,)), front.bool().reshape(shape)
 
@@ -67,10 +68,11 @@ def project_gather(xyz_st, xyz, query_camera, train_imgs, train_cameras, featmap
   mask = torch.empty(R, S, V, 1, device=dev)
   fm = f32c(featmaps)
   ws = _lib.workspace.get(fm.numel() * 4, dev, slot=1)
+  A = Args()
   with torch.cuda.device(dev):
     check(lib.dyn_project_gather(
-        ptr(f32c(xyz_st)), ptr(f32c(xyz)) if xyz is not None else None,
-        ptr(f32c(query_camera)), ptr(f32c(train_imgs)), ptr(f32c(train_cameras)), ptr(fm),
+        A(xyz_st), A(xyz),
+        A(query_camera), A(train_imgs), A(train_cameras), ptr(fm),
         V, R, S, H, W, Cc, h, w, ws.data_ptr(), ptr(rgb_feat), ptr(ray_diff), ptr(mask),
         stream()))
   return rgb_feat, ray_diff, mask

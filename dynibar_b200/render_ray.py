@@ -18,7 +18,7 @@ import torch
 
 from dynibar_b200 import _lib
 from dynibar_b200 import weights as _weights
-from dynibar_b200._lib import lib, ptr, f32c, check, stream, dev_of
+from dynibar_b200._lib import lib, ptr, f32c, check, stream, dev_of, Args
 from dynibar_b200.projection import project_gather
 
 # GEMM precision of the network kernels: _lib.PREC_FP32 (SIMT parity mode) or
@@ -61,10 +61,11 @@ def sample_along_camera_ray(ray_o, ray_d, depth_range, N_samples, inv_uniform=Fa
   pts = torch.empty(R, N_samples, 3, device=dev)
   z = torch.empty(R, N_samples, device=dev)
   s = torch.empty(R, N_samples, device=dev)
+  A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_sample_rays(ptr(f32c(ray_o)), ptr(f32c(ray_d)), near, far, R, N_samples,
+    check(lib.dyn_sample_rays(A(ray_o), A(ray_d), near, far, R, N_samples,
                               int(bool(inv_uniform)),
-                              ptr(f32c(jitter)) if jitter is not None else None,
+                              A(jitter),
                               ptr(pts), ptr(z), ptr(s), stream()))
   return pts, z, s
 
@@ -81,8 +82,9 @@ def points_from_depths(ray_o, ray_d, z_vals, depth_range):
   near, far = _scalar(depth_range[0, 0]), _scalar(depth_range[0, 1])
   pts = torch.empty(R, S, 3, device=dev)
   s = torch.empty(R, S, device=dev)
+  A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_points_from_depths(ptr(f32c(ray_o)), ptr(f32c(ray_d)), ptr(f32c(z_vals)), near,
+    check(lib.dyn_points_from_depths(A(ray_o), A(ray_d), A(z_vals), near,
                                      far, R, S, ptr(pts), ptr(s), stream()))
   return pts, s
 
@@ -100,6 +102,7 @@ def motion_mlp_forward(module, xyzt):
   out = torch.empty(N, 3 * net.num_basis, device=dev)
   nbytes = lib.dyn_motion_workspace_bytes(N, 1)
   ws = _lib.workspace.get(nbytes, dev)
+  A = Args()
   with torch.cuda.device(dev):
     check(lib.dyn_motion_mlp(net.handle, ptr(x), N, ptr(out), ws.data_ptr(), nbytes, PRECISION,
                              stream()))
@@ -117,8 +120,9 @@ def motion_coefficients(module, pts, t):
   out = torch.empty(R, S, 3 * net.num_basis, device=dev)
   nbytes = lib.dyn_motion_workspace_bytes(R, S)
   ws = _lib.workspace.get(nbytes, dev)
+  A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_motion_coeffs(net.handle, ptr(f32c(pts)), float(t), R, S, ptr(out),
+    check(lib.dyn_motion_coeffs(net.handle, A(pts), float(t), R, S, ptr(out),
                                 ws.data_ptr(), nbytes, PRECISION, stream()))
   return out
 
@@ -131,8 +135,9 @@ def displaced_points(pts, coeff, basis, frame_idx, offsets, num_vv=0):
   T, nb = basis.shape
   seq = torch.empty(n_off + num_vv, R, S, 3, device=dev)
   offs = (C.c_int * max(n_off, 1))(*[int(o) for o in offsets])
+  A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_traj_displace(ptr(f32c(pts)), ptr(f32c(coeff)), ptr(f32c(basis).to(dev)), T, nb,
+    check(lib.dyn_traj_displace(A(pts), A(coeff), A(basis.to(dev)), T, nb,
                                 int(frame_idx), offs, n_off, int(num_vv), R, S, ptr(seq), stream()))
   return seq
 
@@ -143,8 +148,9 @@ def displaced_points(pts, coeff, basis, frame_idx, offsets, num_vv=0):
 def compute_ref_plucker_coordinate(ray_o, ray_d):
   R = ray_o.shape[0]
   out = torch.empty(R, 6, device=dev_of(ray_o))
+  A = Args()
   with torch.cuda.device(ray_o.device):
-    check(lib.dyn_plucker_ref(ptr(f32c(ray_o)), ptr(f32c(ray_d)), R, ptr(out), stream()))
+    check(lib.dyn_plucker_ref(A(ray_o), A(ray_d), R, ptr(out), stream()))
   return out
 
 
@@ -153,8 +159,9 @@ def compute_src_plucker_coordinate(pts, src_cameras):
   R, S = pts.shape[:2]
   V = src_cameras.shape[1]
   out = torch.empty(R, S, V, 6, device=dev_of(pts))
+  A = Args()
   with torch.cuda.device(pts.device):
-    check(lib.dyn_plucker_src(ptr(f32c(pts)), ptr(f32c(src_cameras)), V, R, S, ptr(out), stream()))
+    check(lib.dyn_plucker_src(A(pts), A(src_cameras), V, R, S, ptr(out), stream()))
   return out
 
 
@@ -172,9 +179,10 @@ def net_dynamic_forward(module, pts, rgb_feat, ray_dir, mask, time):
   nbytes = lib.dyn_net_workspace_bytes(_lib.NET_DYNAMIC, R, S, V)
   ws = _lib.workspace.get(nbytes, dev)
   t = _scalar(time.float() if torch.is_tensor(time) else time)
+  A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_net_dynamic(net.handle, ptr(f32c(pts)), ptr(f32c(rgb_feat)), ptr(f32c(ray_dir)),
-                              ptr(f32c(mask)), t, R, S, V, ptr(raw), ws.data_ptr(), nbytes,
+    check(lib.dyn_net_dynamic(net.handle, A(pts), A(rgb_feat), A(ray_dir),
+                              A(mask), t, R, S, V, ptr(raw), ws.data_ptr(), nbytes,
                               PRECISION, stream()))
   return raw
 
@@ -188,9 +196,10 @@ def net_static_forward(module, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask
   raw = torch.empty(R, S, 4, device=dev)
   nbytes = lib.dyn_net_workspace_bytes(_lib.NET_STATIC, R, S, V)
   ws = _lib.workspace.get(nbytes, dev)
+  A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_net_static(net.handle, ptr(f32c(pts)), ptr(f32c(ref_rays)), ptr(f32c(src_rays)),
-                             ptr(f32c(rgb_feat)), ptr(f32c(ray_diff)), ptr(f32c(mask)), R, S, V,
+    check(lib.dyn_net_static(net.handle, A(pts), A(ref_rays), A(src_rays),
+                             A(rgb_feat), A(ray_diff), A(mask), R, S, V,
                              ptr(raw), ws.data_ptr(), nbytes, PRECISION, stream()))
   return raw
 
@@ -203,9 +212,10 @@ def _composite(raw_dy, raw_st, z, mask_dy, V_dy, min_dy, mask_st, V_st, min_st):
   dev = dev_of(z)
   rays = torch.empty(R, 11, device=dev)
   samp = torch.empty(5, R, S, device=dev)
+  A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_composite(ptr(f32c(raw_dy)), ptr(f32c(raw_st)), ptr(f32c(z)), ptr(f32c(mask_dy)),
-                            V_dy, min_dy, ptr(f32c(mask_st)), V_st, min_st, R, S, ptr(rays),
+    check(lib.dyn_composite(A(raw_dy), A(raw_st), A(z), A(mask_dy),
+                            V_dy, min_dy, A(mask_st), V_st, min_st, R, S, ptr(rays),
                             ptr(samp), stream()))
   return OrderedDict([
       ("rgb", rays[:, 0:3]), ("rgb_static", rays[:, 3:6]), ("rgb_dy", rays[:, 6:9]),
@@ -220,8 +230,9 @@ def _composite_vanilla(raw, z, mask, V, min_views):
   dev = dev_of(z)
   rays = torch.empty(R, 5, device=dev)
   samp = torch.empty(2, R, S, device=dev)
+  A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_composite_vanilla(ptr(f32c(raw)), ptr(f32c(z)), ptr(f32c(mask)), V, min_views,
+    check(lib.dyn_composite_vanilla(A(raw), A(z), A(mask), V, min_views,
                                     R, S, ptr(rays), ptr(samp), stream()))
   return OrderedDict([
       ("rgb", rays[:, 0:3]), ("depth", rays[:, 3]), ("weights", samp[0]),
@@ -252,9 +263,10 @@ def resample_depths(z_vals, weights, N_importance, inv_uniform, det=True, u=None
   if det:
     u = None
   out = torch.empty(R, S + N_importance, device=dev)
+  A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_resample(ptr(f32c(z_vals)), ptr(f32c(weights)),
-                           ptr(f32c(u)) if u is not None else None, R, S, N_importance,
+    check(lib.dyn_resample(A(z_vals), A(weights),
+                           A(u), R, S, N_importance,
                            int(bool(inv_uniform)), ptr(out), stream()))
   return out
 
@@ -268,11 +280,12 @@ def _flow_sceneflow(weights, pts_seq, src_cameras, uv, coeff, basis, frame_idx, 
   flows = torch.empty(n_flow, R, 2, device=dev)
   exp_sf = torch.empty(R, 3, device=dev) if coeff is not None else None
   T, nb = (basis.shape if basis is not None else (0, 1))
+  A = Args()
   with torch.cuda.device(dev):
     check(lib.dyn_flow_sceneflow(
-        ptr(f32c(weights)), ptr(f32c(pts_seq)), ptr(f32c(src_cameras)), ptr(f32c(uv)),
-        ptr(f32c(coeff)) if coeff is not None else None,
-        ptr(f32c(basis).to(dev)) if basis is not None else None, T, nb, int(frame_idx), int(sf_k),
+        A(weights), A(pts_seq), A(src_cameras), A(uv),
+        A(coeff),
+        A(basis.to(dev) if basis is not None else None), T, nb, int(frame_idx), int(sf_k),
         int(n_flow), R, S, ptr(flows), ptr(exp_sf) if exp_sf is not None else None, stream()))
   return flows, exp_sf
 

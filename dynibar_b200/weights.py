@@ -51,8 +51,8 @@ class PackedNet(object):
 
   def __del__(self):
     h = getattr(self, "handle", None)
-    if h is not None and h.value:
-      _lib.lib.dyn_net_destroy(h)
+    if h is not None and h.value and _lib is not None and getattr(_lib, "lib", None) is not None:
+      _lib.lib.dyn_net_destroy(h)  # (module globals may already be gone at interpreter exit)
       self.handle = None
 
 
