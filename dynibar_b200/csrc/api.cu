@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include "linear_tc.cuh"
 #include "nets.cuh"
 
 namespace dyn {
@@ -54,13 +55,16 @@ size_t dyn_net_param_count(int kind) {
 }
 
 size_t dyn_net_packed_bytes(int kind) {
-  (void)kind;
-  return 0;  // tensor-core operand images: see nets_tc.cu (filled in when that path is linked)
+  switch (kind) {
+    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes;
+    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes;
+    case DYN_NET_MOTION: return (size_t)motion_layout(8).all.packed_bytes;
+    default: return 0;
+  }
 }
 
 int dyn_net_create(int kind, const float* params, size_t n_params, void* packed, int n_samples,
                    float shift, int anti_alias_pooling, int mask_rgb, void* stream, dyn_net_t* out) {
-  (void)stream;
   DYN_CHECK_ARG(out != nullptr && params != nullptr);
   dyn_net* n = (dyn_net*)calloc(1, sizeof(dyn_net));
   if (!n) return fail(DYN_E_INVALID, "out of host memory");
@@ -101,6 +105,14 @@ int dyn_net_create(int kind, const float* params, size_t n_params, void* packed,
     free(n);
     return fail(DYN_E_INVALID, "net kind %d: got %zu parameters, expected %zu", kind, n_params, expect);
   }
+  if (packed != nullptr) {  // tensor-core operand images of every layer
+    const LayerList& ll = kind == DYN_NET_DYNAMIC ? n->dl.all : (kind == DYN_NET_STATIC ? n->sl.all : n->ml.all);
+    for (int i = 0; i < ll.n; ++i) {
+      int rc = tc_pack_weight(params + ll.l[i].w, ll.l[i].out, ll.l[i].in,
+                              reinterpret_cast<char*>(packed) + ll.l[i].tc, (cudaStream_t)stream);
+      if (rc) { free(n); return rc; }
+    }
+  }
   *out = n;
   return DYN_OK;
 }
@@ -120,9 +132,9 @@ int dyn_motion_coeffs(dyn_net_t motion, const float* pts, float time, int R, int
                       void* workspace, size_t workspace_bytes, int precision, void* stream) {
   DYN_CHECK_ARG(motion && motion->kind == DYN_NET_MOTION && pts && coeff && workspace);
   DYN_CHECK_ARG(R >= 0 && S >= 1);
-  if (precision != DYN_PREC_FP32) return fail(DYN_E_INVALID, "precision %d not built", precision);
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = motion_f32(motion, pts, 3, false, time, (long long)R * S, coeff, workspace, workspace_bytes, st);
+  int rc = motion_f32(motion, pts, 3, false, time, (long long)R * S, coeff, workspace, workspace_bytes, precision, st);
   if (rc) return rc;
   return zero_last_samples(coeff, R, S, 3 * motion->nb, st);
 }
@@ -130,8 +142,9 @@ int dyn_motion_coeffs(dyn_net_t motion, const float* pts, float time, int R, int
 int dyn_motion_mlp(dyn_net_t motion, const float* xyzt, int N, float* coeff, void* workspace,
                    size_t workspace_bytes, int precision, void* stream) {
   DYN_CHECK_ARG(motion && motion->kind == DYN_NET_MOTION && xyzt && coeff && workspace && N >= 0);
-  if (precision != DYN_PREC_FP32) return fail(DYN_E_INVALID, "precision %d not built", precision);
-  return motion_f32(motion, xyzt, 4, true, 0.f, N, coeff, workspace, workspace_bytes, (cudaStream_t)stream);
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
+  return motion_f32(motion, xyzt, 4, true, 0.f, N, coeff, workspace, workspace_bytes, precision,
+                    (cudaStream_t)stream);
 }
 
 int dyn_net_dynamic(dyn_net_t net, const float* pts, const float* rgb_feat, const float* ray_dir,
@@ -139,9 +152,9 @@ int dyn_net_dynamic(dyn_net_t net, const float* pts, const float* rgb_feat, cons
                     size_t workspace_bytes, int precision, void* stream) {
   DYN_CHECK_ARG(net && net->kind == DYN_NET_DYNAMIC && pts && rgb_feat && ray_dir && mask && raw);
   DYN_CHECK_ARG(workspace && R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
-  if (precision != DYN_PREC_FP32) return fail(DYN_E_INVALID, "precision %d not built", precision);
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
   return net_dynamic_f32(net, pts, rgb_feat, ray_dir, mask, time, R, S, V, raw, workspace,
-                         workspace_bytes, (cudaStream_t)stream);
+                         workspace_bytes, precision, (cudaStream_t)stream);
 }
 
 int dyn_net_static(dyn_net_t net, const float* pts, const float* ref_rays, const float* src_rays,
@@ -149,9 +162,9 @@ int dyn_net_static(dyn_net_t net, const float* pts, const float* ref_rays, const
                    float* raw, void* workspace, size_t workspace_bytes, int precision, void* stream) {
   DYN_CHECK_ARG(net && net->kind == DYN_NET_STATIC && pts && ref_rays && src_rays && rgb_feat);
   DYN_CHECK_ARG(ray_diff && mask && raw && workspace && R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
-  if (precision != DYN_PREC_FP32) return fail(DYN_E_INVALID, "precision %d not built", precision);
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
   return net_static_f32(net, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask, R, S, V, raw, workspace,
-                        workspace_bytes, (cudaStream_t)stream);
+                        workspace_bytes, precision, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -50,6 +50,12 @@ struct LinearP {
   int w;  // offset of weight [out, in]
   int b;  // offset of bias [out] or -1
   int in, out;
+  long long tc;  // byte offset of the packed tensor-core image in dyn_net::packed
+};
+struct LayerList {
+  LinearP l[32];
+  int n;
+  long long packed_bytes;
 };
 
 struct DynamicLayout {
@@ -58,6 +64,7 @@ struct DynamicLayout {
   int ln_w, ln_b;
   LinearP refpts0, refpts2, outgeo0, outgeo2, rgb0, rgb2, rgb4;
   int total;
+  LayerList all;
 };
 struct StaticLayout {
   int s;  // scalar anti-alias parameter (present iff anti_alias_pooling)
@@ -66,11 +73,13 @@ struct StaticLayout {
   int ln_w, ln_b;
   LinearP outgeo0, outgeo2, rgb0, rgb2, rgb4;
   int total;
+  LayerList all;
 };
 struct MotionLayout {
   LinearP pts[8];
   LinearP coeff;
   int total;
+  LayerList all;
 };
 
 DynamicLayout dynamic_layout();

@@ -12,12 +12,12 @@ size_t net_static_f32_workspace(int R, int S, int V);
 size_t motion_f32_workspace(long long N);
 int net_dynamic_f32(const dyn_net* n, const float* pts, const float* rgb_feat, const float* ray_dir,
                     const float* mask, float time, int R, int S, int V, float* raw, void* ws,
-                    size_t ws_bytes, cudaStream_t st);
+                    size_t ws_bytes, int prec, cudaStream_t st);
 int net_static_f32(const dyn_net* n, const float* pts, const float* ref_rays, const float* src_rays,
                    const float* rgb_feat, const float* ray_diff, const float* mask, int R, int S, int V,
-                   float* raw, void* ws, size_t ws_bytes, cudaStream_t st);
+                   float* raw, void* ws, size_t ws_bytes, int prec, cudaStream_t st);
 int motion_f32(const dyn_net* n, const float* x, int ldx, bool time_is_column, float time, long long N,
-               float* coeff, void* ws, size_t ws_bytes, cudaStream_t st);
+               float* coeff, void* ws, size_t ws_bytes, int prec, cudaStream_t st);
 int zero_last_samples(float* coeff, int R, int S, int width, cudaStream_t st);
 
 }  // namespace dyn

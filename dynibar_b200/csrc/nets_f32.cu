@@ -1,11 +1,12 @@
-// DYN_PREC_FP32 evaluation of the three networks (a3, a8-a11): the reference's
-// op graph restated as fp32 SIMT kernels -- generic tiled linear layers
-// (linear_f32.cu) plus the fused glue below (positional encodings, view
+// Staged evaluation of the three networks (a3, a8-a11): the reference's op
+// graph as one kernel per layer -- generic linear layers (fp32 SIMT in
+// linear_f32.cu for DYN_PREC_FP32, tcgen05 in linear_tc.cu for DYN_PREC_BF16)
+// plus the fused fp32 glue below (positional encodings, view
 // pooling, visibility gating, ray transformer, heads).  This is the parity
 // mode; the throughput mode is the tcgen05 path in nets_tc.cu.
 #include <math.h>
 
-#include "linear_f32.cuh"
+#include "linear_tc.cuh"
 #include "nets.cuh"
 
 namespace dyn {
@@ -13,17 +14,24 @@ namespace dyn {
 // ---------------------------------------------------------------------------
 // layouts
 // ---------------------------------------------------------------------------
+static LayerList* g_list = nullptr;  // layout being built (host, single-threaded at create time)
+
 static LinearP take(int& off, int out, int in, bool bias = true) {
   LinearP l;
   l.in = in; l.out = out;
   l.w = off; off += out * in;
   if (bias) { l.b = off; off += out; } else { l.b = -1; }
+  l.tc = g_list->packed_bytes;
+  g_list->packed_bytes += (long long)((tc_packed_bytes(out, in) + 255) & ~(size_t)255);
+  g_list->l[g_list->n++] = l;
   return l;
 }
 
 DynamicLayout dynamic_layout() {
   DynamicLayout L;
   int o = 0;
+  L.all.n = 0; L.all.packed_bytes = 0;
+  g_list = &L.all;
   L.ray_dir0 = take(o, 256, 21); L.ray_dir2 = take(o, kF, 256);
   L.base0 = take(o, 256, 3 * kF); L.base2 = take(o, 128, 256);
   L.vis0 = take(o, 128, 128); L.vis2 = take(o, 129, 128);
@@ -42,6 +50,8 @@ DynamicLayout dynamic_layout() {
 StaticLayout static_layout(bool anti_alias) {
   StaticLayout L;
   int o = 0;
+  L.all.n = 0; L.all.packed_bytes = 0;
+  g_list = &L.all;
   L.s = -1;
   if (anti_alias) { L.s = o; o += 1; }
   L.ray_dir0 = take(o, 256, 103); L.ray_dir2 = take(o, kF, 256);
@@ -62,6 +72,8 @@ StaticLayout static_layout(bool anti_alias) {
 MotionLayout motion_layout(int nb) {
   MotionLayout L;
   int o = 0;
+  L.all.n = 0; L.all.packed_bytes = 0;
+  g_list = &L.all;
   L.pts[0] = take(o, 256, 132);
   for (int i = 1; i < 8; ++i) L.pts[i] = take(o, 256, i == 5 ? 388 : 256);
   L.coeff = take(o, 3 * nb, 256);
@@ -476,6 +488,14 @@ struct Bump {
 };
 
 static const float* P_(const dyn_net* n, int off) { return off < 0 ? nullptr : n->params + off; }
+
+// one linear layer in the requested precision: tcgen05 (bf16 operands) when the
+// net carries packed images and the layer is big enough to fill a UMMA tile
+static int run_lin(const dyn_net* n, const LinearP& l, const LinArgs& a, int prec, cudaStream_t st) {
+  if (prec == DYN_PREC_BF16 && n->packed != nullptr && a.M >= 128 && l.out >= 16)
+    return launch_linear_tc(a, reinterpret_cast<const char*>(n->packed) + l.tc, st);
+  return launch_linear(a, st);
+}
 static LinArgs L1(const dyn_net* n, const LinearP& l, const float* X, float* Y, long long M, int act) {
   return lin1(X, l.in, P_(n, l.w), P_(n, l.b), Y, l.out, M, l.out, l.in, act);
 }
@@ -508,39 +528,39 @@ static void trunk_alloc(Bump& b, long long M, long long P, TrunkBufs* t) {
 template <class Layout>
 static int run_trunk(const dyn_net* n, const Layout& L, const Seg& mv, const Seg& feat,
                      const float* weight1, const float* mask, long long M, long long P, int R,
-                     int S, int V, bool add_posenc, TrunkBufs& t, cudaStream_t st) {
+                     int S, int V, bool add_posenc, TrunkBufs& t, int prec, cudaStream_t st) {
   // base_fc (mlp_network.py:270 / :483)
   LinArgs a = L1(n, L.base0, nullptr, t.H1, M, ACT_ELU);
   a.seg[0] = mv; a.seg[1] = feat; a.nseg = 2;
-  RUN(launch_linear(a, st));
-  RUN(launch_linear(L1(n, L.base2, t.H1, t.X, M, ACT_ELU), st));
+  RUN(run_lin(n, L.base0, a, prec, st));
+  RUN(run_lin(n, L.base2, L1(n, L.base2, t.H1, t.X, M, ACT_ELU), prec, st));
   // vis_fc(x * weight) (:272 / :485)
   a = L1(n, L.vis0, t.X, t.H2, M, ACT_ELU);
   a.row_scale = weight1;
-  RUN(launch_linear(a, st));
-  RUN(launch_linear(L1(n, L.vis2, t.H2, t.XV, M, ACT_ELU), st));
+  RUN(run_lin(n, L.vis0, a, prec, st));
+  RUN(run_lin(n, L.vis2, L1(n, L.vis2, t.H2, t.XV, M, ACT_ELU), prec, st));
   vis1_kernel<<<cdiv(M * 128, 256), 256, 0, st>>>(t.X, t.XV, mask, M, t.vis1);
   DYN_LAUNCH_CHECK();
   // vis_fc2(x * vis) (:276 / :489)
   a = L1(n, L.vis2_0, t.X, t.H2, M, ACT_ELU);
   a.row_scale = t.vis1;
-  RUN(launch_linear(a, st));
-  RUN(launch_linear(L1(n, L.vis2_2, t.H2, t.vis2, M, ACT_SIGMOID), st));
+  RUN(run_lin(n, L.vis2_0, a, prec, st));
+  RUN(run_lin(n, L.vis2_2, L1(n, L.vis2_2, t.H2, t.vis2, M, ACT_SIGMOID), prec, st));
   pool2_kernel<<<cdiv(P * 128, 256), 256, 0, st>>>(t.X, t.vis2, mask, P, V, t.G, t.nvalid);
   DYN_LAUNCH_CHECK();
   mask_vis2_kernel<<<cdiv(M, 256), 256, 0, st>>>(t.vis2, mask, M);
   DYN_LAUNCH_CHECK();
   // geometry_fc (:283 / :496)
-  RUN(launch_linear(L1(n, L.geo0, t.G, t.GH, P, ACT_ELU), st));
-  RUN(launch_linear(L1(n, L.geo2, t.GH, t.G2, P, ACT_ELU), st));
+  RUN(run_lin(n, L.geo0, L1(n, L.geo0, t.G, t.GH, P, ACT_ELU), prec, st));
+  RUN(run_lin(n, L.geo2, L1(n, L.geo2, t.GH, t.G2, P, ACT_ELU), prec, st));
   if (add_posenc) {
     add_posenc_kernel<<<cdiv(P * 128, 256), 256, 0, st>>>(t.G2, P, S);
     DYN_LAUNCH_CHECK();
   }
   // ray transformer (:287 / :500)
-  RUN(launch_linear(L1(n, L.wq, t.G2, t.Q, P, ACT_NONE), st));
-  RUN(launch_linear(L1(n, L.wk, t.G2, t.K, P, ACT_NONE), st));
-  RUN(launch_linear(L1(n, L.wv, t.G2, t.V, P, ACT_NONE), st));
+  RUN(run_lin(n, L.wq, L1(n, L.wq, t.G2, t.Q, P, ACT_NONE), prec, st));
+  RUN(run_lin(n, L.wk, L1(n, L.wk, t.G2, t.K, P, ACT_NONE), prec, st));
+  RUN(run_lin(n, L.wv, L1(n, L.wv, t.G2, t.V, P, ACT_NONE), prec, st));
   {
     int threads = ((S + 31) / 32) * 32;
     size_t smem = (size_t)2 * S * 33 * sizeof(float);
@@ -551,7 +571,7 @@ static int run_trunk(const dyn_net* n, const Layout& L, const Seg& mv, const Seg
     attention_kernel<<<R, threads, smem, st>>>(t.Q, t.K, t.V, t.nvalid, S, t.O);
     DYN_LAUNCH_CHECK();
   }
-  RUN(launch_linear(L1(n, L.fc, t.O, t.O2, P, ACT_NONE), st));
+  RUN(run_lin(n, L.fc, L1(n, L.fc, t.O, t.O2, P, ACT_NONE), prec, st));
   resid_ln_kernel<<<cdiv(P * 32, 256), 256, 0, st>>>(t.O2, t.G2, P_(n, L.ln_w), P_(n, L.ln_b), P, t.G3);
   DYN_LAUNCH_CHECK();
   return DYN_OK;
@@ -585,7 +605,7 @@ size_t net_dynamic_f32_workspace(int R, int S, int V) {
 
 int net_dynamic_f32(const dyn_net* n, const float* pts, const float* rgb_feat, const float* ray_dir,
                     const float* mask, float time, int R_all, int S, int V, float* raw, void* ws,
-                    size_t ws_bytes, cudaStream_t st) {
+                    size_t ws_bytes, int prec, cudaStream_t st) {
   const DynamicLayout& L = n->dl;
   const int RC = net_rows_per_chunk(S, V);
   for (int r0 = 0; r0 < R_all; r0 += RC) {
@@ -603,23 +623,23 @@ int net_dynamic_f32(const dyn_net* n, const float* pts, const float* rgb_feat, c
     dyn_pool1_kernel<<<cdiv(P * kF, 256), 256, 0, st>>>(c_feat, d.dfeat, c_mask, P, V, d.feat, d.mv, d.w1);
     DYN_LAUNCH_CHECK();
     RUN(run_trunk(n, L, Seg{d.mv, 2 * kF, 2 * kF, V}, Seg{d.feat, kF, kF, 1}, d.w1, c_mask, M, P, R, S,
-                  V, /*add_posenc=*/true, d.t, st));
+                  V, /*add_posenc=*/true, d.t, prec, st));
     // ref_pts_fc(cat[g, PE(pts)]) (:291-292)
     RUN(launch_pe(c_pts, 3, 3, 0, 0.f, 5, false, P, d.ptspe, st));
     LinArgs a = L1(n, L.refpts0, nullptr, d.G4h, P, ACT_ELU);
     a.seg[0] = Seg{d.t.G3, 128, 128, 1}; a.seg[1] = Seg{d.ptspe, 33, 33, 1}; a.nseg = 2;
-    RUN(launch_linear(a, st));
-    RUN(launch_linear(L1(n, L.refpts2, d.G4h, d.G4, P, ACT_ELU), st));
+    RUN(run_lin(n, L.refpts0, a, prec, st));
+    RUN(run_lin(n, L.refpts2, L1(n, L.refpts2, d.G4h, d.G4, P, ACT_ELU), prec, st));
     // sigma head (:294-299)
-    RUN(launch_linear(L1(n, L.outgeo0, d.G4, d.sh, P, ACT_ELU), st));
-    RUN(launch_linear(L1(n, L.outgeo2, d.sh, d.sig, P, ACT_NONE), st));
+    RUN(run_lin(n, L.outgeo0, L1(n, L.outgeo0, d.G4, d.sh, P, ACT_ELU), prec, st));
+    RUN(run_lin(n, L.outgeo2, L1(n, L.outgeo2, d.sh, d.sig, P, ACT_NONE), prec, st));
     // rgb head (:301-314)
     RUN(launch_pe(ray_dir + (long long)r0 * 3, 3, 3, 0, 0.f, 4, false, R, d.dirpe, st));
     a = L1(n, L.rgb0, nullptr, d.ch, P, ACT_ELU);
     a.seg[0] = Seg{d.G4, 128, 128, 1}; a.seg[1] = Seg{d.dirpe, 27, 27, S}; a.nseg = 2;
-    RUN(launch_linear(a, st));
-    RUN(launch_linear(L1(n, L.rgb2, d.ch, d.ch2, P, ACT_ELU), st));
-    RUN(launch_linear(L1(n, L.rgb4, d.ch2, d.rgb, P, ACT_SIGMOID), st));
+    RUN(run_lin(n, L.rgb0, a, prec, st));
+    RUN(run_lin(n, L.rgb2, L1(n, L.rgb2, d.ch, d.ch2, P, ACT_ELU), prec, st));
+    RUN(run_lin(n, L.rgb4, L1(n, L.rgb4, d.ch2, d.rgb, P, ACT_SIGMOID), prec, st));
     dyn_out_kernel<<<cdiv(P, 256), 256, 0, st>>>(d.rgb, d.sig, d.t.nvalid, n->shift, P, raw + p0 * 4);
     DYN_LAUNCH_CHECK();
   }
@@ -654,7 +674,7 @@ size_t net_static_f32_workspace(int R, int S, int V) {
 
 int net_static_f32(const dyn_net* n, const float* pts, const float* ref_rays, const float* src_rays,
                    const float* rgb_feat, const float* ray_diff, const float* mask, int R_all, int S,
-                   int V, float* raw, void* ws, size_t ws_bytes, cudaStream_t st) {
+                   int V, float* raw, void* ws, size_t ws_bytes, int prec, cudaStream_t st) {
   const StaticLayout& L = n->sl;
   const int RC = net_rows_per_chunk(S, V);
   for (int r0 = 0; r0 < R_all; r0 += RC) {
@@ -675,26 +695,26 @@ int net_static_f32(const dyn_net* n, const float* pts, const float* ref_rays, co
     LinArgs a = L1(n, L.ray_dir0, nullptr, d.H0, M, ACT_ELU);
     a.seg[0] = Seg{d.ptspe, 33, 33, V}; a.seg[1] = Seg{d.srcpe, 66, 66, 1};
     a.seg[2] = Seg{c_rd, 4, 4, 1}; a.nseg = 3;
-    RUN(launch_linear(a, st));
-    RUN(launch_linear(L1(n, L.ray_dir2, d.H0, d.SF, M, ACT_NONE), st));
+    RUN(run_lin(n, L.ray_dir0, a, prec, st));
+    RUN(run_lin(n, L.ray_dir2, L1(n, L.ray_dir2, d.H0, d.SF, M, ACT_NONE), prec, st));
     // ref_feat = ref_feature_fc(ref_pe) per ray (:450)
-    RUN(launch_linear(L1(n, L.ref_feat, d.refpe, d.reff, R, ACT_NONE), st));
+    RUN(run_lin(n, L.ref_feat, L1(n, L.ref_feat, d.refpe, d.reff, R, ACT_NONE), prec, st));
     st_pool1_kernel<<<cdiv(P * 2 * kF, 256), 256, 0, st>>>(
         c_feat, d.SF, d.reff, c_rd, c_mask, n->anti_alias ? n->params + L.s : nullptr, n->mask_rgb, P,
         S, V, d.feat70, d.mv, d.w1, d.meff);
     DYN_LAUNCH_CHECK();
     RUN(run_trunk(n, L, Seg{d.mv, 4 * kF, 4 * kF, V}, Seg{d.feat70, 2 * kF, 2 * kF, 1}, d.w1, d.meff,
-                  M, P, R, S, V, /*add_posenc=*/false, d.t, st));
+                  M, P, R, S, V, /*add_posenc=*/false, d.t, prec, st));
     // sigma head (:503-506)
-    RUN(launch_linear(L1(n, L.outgeo0, d.t.G3, d.sh, P, ACT_ELU), st));
-    RUN(launch_linear(L1(n, L.outgeo2, d.sh, d.sig, P, ACT_NONE), st));
+    RUN(run_lin(n, L.outgeo0, L1(n, L.outgeo0, d.t.G3, d.sh, P, ACT_ELU), prec, st));
+    RUN(run_lin(n, L.outgeo2, L1(n, L.outgeo2, d.sh, d.sig, P, ACT_NONE), prec, st));
     // rgb blending head on [g, x, vis, ray_diff] (:508-525)
     a = L1(n, L.rgb0, nullptr, d.ch, M, ACT_ELU);
     a.seg[0] = Seg{d.t.G3, 128, 128, V}; a.seg[1] = Seg{d.t.X, 128, 128, 1};
     a.seg[2] = Seg{d.t.vis2, 1, 1, 1}; a.seg[3] = Seg{c_rd, 4, 4, 1}; a.nseg = 4;
-    RUN(launch_linear(a, st));
-    RUN(launch_linear(L1(n, L.rgb2, d.ch, d.ch2, M, ACT_ELU), st));
-    RUN(launch_linear(L1(n, L.rgb4, d.ch2, d.logit, M, ACT_NONE), st));
+    RUN(run_lin(n, L.rgb0, a, prec, st));
+    RUN(run_lin(n, L.rgb2, L1(n, L.rgb2, d.ch, d.ch2, M, ACT_ELU), prec, st));
+    RUN(run_lin(n, L.rgb4, L1(n, L.rgb4, d.ch2, d.logit, M, ACT_NONE), prec, st));
     st_out_kernel<<<cdiv(P, 256), 256, 0, st>>>(d.logit, d.meff, c_feat, d.sig, d.t.nvalid, P, V,
                                                 raw + p0 * 4);
     DYN_LAUNCH_CHECK();
@@ -716,7 +736,7 @@ size_t motion_f32_workspace(long long N) {
 
 // xyz [N,3] + constant time, or xyzt [N,4] when time_is_column
 int motion_f32(const dyn_net* n, const float* x, int ldx, bool time_is_column, float time,
-               long long N_all, float* coeff, void* ws, size_t ws_bytes, cudaStream_t st) {
+               long long N_all, float* coeff, void* ws, size_t ws_bytes, int prec, cudaStream_t st) {
   const MotionLayout& L = n->ml;
   for (long long i0 = 0; i0 < N_all; i0 += kMotionRows) {
     long long N = (N_all - i0) < kMotionRows ? (N_all - i0) : kMotionRows;
@@ -730,7 +750,7 @@ int motion_f32(const dyn_net* n, const float* x, int ldx, bool time_is_column, f
     else
       RUN(launch_pe(x + i0 * ldx, 3, ldx, 1, time, 16, true, N, X0, st));
     float *cur = A, *nxt = B;
-    RUN(launch_linear(L1(n, L.pts[0], X0, cur, N, ACT_RELU), st));
+    RUN(run_lin(n, L.pts[0], L1(n, L.pts[0], X0, cur, N, ACT_RELU), prec, st));
     for (int i = 1; i < 8; ++i) {
       LinArgs a = L1(n, L.pts[i], cur, nxt, N, ACT_RELU);
       if (i == 5) {  // skip connection: input is cat([input_pts, h]) (:612-613)
@@ -738,10 +758,10 @@ int motion_f32(const dyn_net* n, const float* x, int ldx, bool time_is_column, f
         a.seg[1] = Seg{cur, 256, 256, 1};
         a.nseg = 2;
       }
-      RUN(launch_linear(a, st));
+      RUN(run_lin(n, L.pts[i], a, prec, st));
       float* t = cur; cur = nxt; nxt = t;
     }
-    RUN(launch_linear(L1(n, L.coeff, cur, coeff + i0 * L.coeff.out, N, ACT_NONE), st));
+    RUN(run_lin(n, L.coeff, L1(n, L.coeff, cur, coeff + i0 * L.coeff.out, N, ACT_NONE), prec, st));
   }
   return DYN_OK;
 }

@@ -176,6 +176,17 @@ int dyn_flow_sceneflow(const float* weights, const float* pts_seq,
                        int frame_idx, int sf_k, int n_flow, int R, int S,
                        float* flows, float* exp_sf, void* stream);
 
+/* ---- building block: one nn.Linear on the tensor cores -----------------------
+ * Y[M,N] = act(X[M,K] W[N,K]^T + b) with bf16 operands / fp32 accumulation
+ * (tcgen05).  act: 0 none, 1 ELU, 2 ReLU, 3 sigmoid.  N <= 256.  packed_ws must
+ * hold dyn_linear_tc_packed_bytes(N, K) bytes (bf16 UMMA image of W).  This is
+ * the kernel behind every nn.Linear of mlp_network.py in DYN_PREC_BF16 mode;
+ * exported for unit testing. */
+size_t dyn_linear_tc_packed_bytes(int N, int K);
+int dyn_linear_tc(const float* X, int ldx, const float* W, const float* b, int M,
+                  int N, int K, int act, float* Y, int ldy, void* packed_ws,
+                  size_t packed_ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
