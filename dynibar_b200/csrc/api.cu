@@ -4,6 +4,7 @@
 
 #include "linear_tc.cuh"
 #include "nets.cuh"
+#include "nets_fused.cuh"
 
 namespace dyn {
 
@@ -56,8 +57,8 @@ size_t dyn_net_param_count(int kind) {
 
 size_t dyn_net_packed_bytes(int kind) {
   switch (kind) {
-    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes;
-    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes;
+    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes + fused_view_bytes(kind);
+    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes + fused_view_bytes(kind);
     case DYN_NET_MOTION: return (size_t)motion_layout(8).all.packed_bytes;
     default: return 0;
   }
@@ -112,6 +113,18 @@ int dyn_net_create(int kind, const float* params, size_t n_params, void* packed,
                               reinterpret_cast<char*>(packed) + ll.l[i].tc, (cudaStream_t)stream);
       if (rc) { free(n); return rc; }
     }
+    if (kind != DYN_NET_MOTION) {  // fused per-view images: packed on the host once
+      float* hp = (float*)malloc(n_params * sizeof(float));
+      if (!hp) { free(n); return fail(DYN_E_INVALID, "out of host memory"); }
+      cudaError_t e = cudaMemcpyAsync(hp, params, n_params * sizeof(float), cudaMemcpyDeviceToHost,
+                                      (cudaStream_t)stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+      int rc = e == cudaSuccess ? fused_view_build(n, hp, reinterpret_cast<char*>(packed) + ll.packed_bytes,
+                                                   fused_view_bytes(kind), (cudaStream_t)stream)
+                                : fail(DYN_E_CUDA, "reading parameters back: %s", cudaGetErrorString(e));
+      free(hp);
+      if (rc) { free(n); return rc; }
+    }
   }
   *out = n;
   return DYN_OK;
@@ -126,6 +139,42 @@ size_t dyn_net_workspace_bytes(int kind, int R, int S, int V) {
   if (kind == DYN_NET_STATIC) return net_static_f32_workspace(R, S, V);
   if (kind == DYN_NET_MOTION) return motion_f32_workspace((long long)R * S);
   return 0;
+}
+
+size_t dyn_net_fused_workspace_bytes(int kind, int R, int S, int V) {
+  return net_fused_workspace(kind, R, S, V);
+}
+
+int dyn_featmaps_channels_last(const float* featmaps, float* out, int V, int C, int h, int w,
+                               void* stream) {
+  DYN_CHECK_ARG(featmaps && out && V >= 1 && C >= 1 && h >= 1 && w >= 1);
+  return launch_to_channels_last(featmaps, out, V, C, h * w, (cudaStream_t)stream);
+}
+
+int dyn_net_static_fused(dyn_net_t net, const float* pts, const float* ray_o, const float* ray_d,
+                         const float* query_cam, const float* src_rgbs, const float* src_cams,
+                         const float* feat_cl, int R, int S, int V, int H, int W, int C, int h, int w,
+                         float* raw, float* mask_out, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  DYN_CHECK_ARG(net && net->kind == DYN_NET_STATIC && pts && ray_o && ray_d && query_cam && src_rgbs);
+  DYN_CHECK_ARG(src_cams && feat_cl && raw && mask_out && workspace && C == kC);
+  DYN_CHECK_ARG(R >= 0 && S >= 1 && V >= 1 && V <= 16);
+  if (R == 0) return DYN_OK;
+  return net_static_fused(net, pts, ray_o, ray_d, query_cam, src_rgbs, src_cams, feat_cl, R, S, V, H, W,
+                          h, w, raw, mask_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dyn_net_dynamic_fused(dyn_net_t net, const float* pts, const float* pts_seq, const float* ray_dir,
+                          const float* query_cam, const float* src_rgbs, const float* src_cams,
+                          const float* feat_cl, float time, int R, int S, int V, int H, int W, int C,
+                          int h, int w, float* raw, float* mask_out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  DYN_CHECK_ARG(net && net->kind == DYN_NET_DYNAMIC && pts && pts_seq && ray_dir && query_cam);
+  DYN_CHECK_ARG(src_rgbs && src_cams && feat_cl && raw && mask_out && workspace && C == kC);
+  DYN_CHECK_ARG(R >= 0 && S >= 1 && V >= 1 && V <= 16);
+  if (R == 0) return DYN_OK;
+  return net_dynamic_fused(net, pts, pts_seq, ray_dir, query_cam, src_rgbs, src_cams, feat_cl, time, R, S,
+                           V, H, W, h, w, raw, mask_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int dyn_motion_coeffs(dyn_net_t motion, const float* pts, float time, int R, int S, float* coeff,

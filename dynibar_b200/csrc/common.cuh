@@ -100,6 +100,10 @@ struct dyn_net {
   dyn::DynamicLayout dl;
   dyn::StaticLayout sl;
   dyn::MotionLayout ml;
+  // fused per-view tensor-core stage (nets_fused.cu): weight images + chunk table
+  void* fused_img;
+  void* fused_tab;
+  int fused_nchunks;
 };
 
 // ---- device helpers ---------------------------------------------------------

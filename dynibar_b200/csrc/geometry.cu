@@ -3,6 +3,7 @@
 // coordinates (a7), optical flow / expected scene flow (a14).
 // All fp32.  Reference file:line citations are relative to /root/reference.
 #include "common.cuh"
+#include "geometry.cuh"
 
 namespace dyn {
 
@@ -107,13 +108,6 @@ __global__ void traj_displace_kernel(const float* __restrict__ pts, const float*
 // ---------------------------------------------------------------------------
 // a4-a6 projection + gather
 // ---------------------------------------------------------------------------
-struct ViewCams {
-  float P[kMaxViews][12];   // rows 0..2 of K * inv(c2w)  (projection.py:46-48)
-  float center[kMaxViews][3];  // c2w[:3,3]
-  float tgt[3];             // target camera centre
-  float h_img, w_img;       // train_cameras[0][:2] (projection.py:136)
-};
-
 // featmaps [V,C,h,w] -> channels-last [V,h,w,C] so one bilinear tap is 128
 // contiguous bytes.
 __global__ void to_channels_last_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
@@ -132,17 +126,6 @@ __global__ void to_channels_last_kernel(const float* __restrict__ in, float* __r
     int p = p0 + j, c = c0 + threadIdx.x;
     if (c < C && p < hw) dst[(long long)p * C + c] = tile[threadIdx.x][j];
   }
-}
-
-__device__ __forceinline__ void project_point(const float* P, float x, float y, float z, float& u,
-                                              float& v, bool& front) {
-  float px = P[0] * x + P[1] * y + P[2] * z + P[3];
-  float py = P[4] * x + P[5] * y + P[6] * z + P[7];
-  float pz = P[8] * x + P[9] * y + P[10] * z + P[11];
-  float d = fmaxf(pz, 1e-8f);  // clamp(min=1e-8), projection.py:51-53
-  u = fminf(fmaxf(px / d, -1e6f), 1e6f);
-  v = fminf(fmaxf(py / d, -1e6f), 1e6f);
-  front = pz > 0.f;
 }
 
 // 8 lanes cooperate on one (point, view) pair: lane j gathers feature
@@ -417,6 +400,13 @@ int build_view_cams(const float* src_cams, int V, const float* query_cam, cudaSt
       }
     for (int i = 0; i < 3; ++i) vc->center[v][i] = c[18 + i * 4 + 3];
   }
+  return DYN_OK;
+}
+
+int launch_to_channels_last(const float* featmaps, float* out, int V, int C, int hw, cudaStream_t st) {
+  dim3 tb(32, 8), tg(cdiv(hw, 32), cdiv(C, 32), V);
+  to_channels_last_kernel<<<tg, tb, 0, st>>>(featmaps, out, C, hw);
+  DYN_LAUNCH_CHECK();
   return DYN_OK;
 }
 

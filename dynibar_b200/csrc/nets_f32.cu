@@ -8,6 +8,7 @@
 
 #include "linear_tc.cuh"
 #include "nets.cuh"
+#include "nets_fused.cuh"
 
 namespace dyn {
 
@@ -411,7 +412,7 @@ __global__ void dyn_out_kernel(const float* __restrict__ rgb, const float* __res
 // the gathered source colours (mlp_network.py:503-526)
 __global__ void st_out_kernel(const float* __restrict__ logit, const float* __restrict__ mask_eff,
                               const float* __restrict__ rgb_feat, const float* __restrict__ sigma,
-                              const float* __restrict__ nvalid, long long P, int V,
+                              const float* __restrict__ nvalid, long long P, int V, int ldf,
                               float* __restrict__ raw) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
@@ -427,7 +428,7 @@ __global__ void st_out_kernel(const float* __restrict__ logit, const float* __re
   float r = 0.f, g = 0.f, b = 0.f;
   for (int v = 0; v < V; ++v) {
     float w = l[v] / den;
-    const float* c = rgb_feat + (p * V + v) * kF;
+    const float* c = rgb_feat + (p * V + v) * ldf;
     r += c[0] * w; g += c[1] * w; b += c[2] * w;
   }
   float4 o = make_float4(r, g, b, nvalid[p] < 1.f ? -1e9f : sigma[p]);
@@ -525,6 +526,42 @@ static void trunk_alloc(Bump& b, long long M, long long P, TrunkBufs* t) {
   t->V = b.f(P * 128); t->O = b.f(P * 128); t->O2 = b.f(P * 128); t->G3 = b.f(P * 128);
 }
 
+// per-point tail shared by the staged and the fused paths:
+// geometry_fc -> (+ sinusoid) -> ray transformer -> t.G3   (mlp_network.py:283-289 / :496-502)
+template <class Layout>
+static int run_point_tail(const dyn_net* n, const Layout& L, const float* G, int ldg, long long P,
+                          int R, int S, bool add_posenc, TrunkBufs& t, int prec, cudaStream_t st) {
+  // geometry_fc (:283 / :496)
+  {
+    LinArgs ga = L1(n, L.geo0, G, t.GH, P, ACT_ELU);
+    ga.seg[0].ld = ldg;
+    RUN(run_lin(n, L.geo0, ga, prec, st));
+  }
+  RUN(run_lin(n, L.geo2, L1(n, L.geo2, t.GH, t.G2, P, ACT_ELU), prec, st));
+  if (add_posenc) {
+    add_posenc_kernel<<<cdiv(P * 128, 256), 256, 0, st>>>(t.G2, P, S);
+    DYN_LAUNCH_CHECK();
+  }
+  // ray transformer (:287 / :500)
+  RUN(run_lin(n, L.wq, L1(n, L.wq, t.G2, t.Q, P, ACT_NONE), prec, st));
+  RUN(run_lin(n, L.wk, L1(n, L.wk, t.G2, t.K, P, ACT_NONE), prec, st));
+  RUN(run_lin(n, L.wv, L1(n, L.wv, t.G2, t.V, P, ACT_NONE), prec, st));
+  {
+    int threads = ((S + 31) / 32) * 32;
+    size_t smem = (size_t)2 * S * 33 * sizeof(float);
+    if (threads > 1024) return fail(DYN_E_INVALID, "ray transformer supports S <= 1024 (got %d)", S);
+    if (smem > 48 * 1024)
+      DYN_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    attention_kernel<<<R, threads, smem, st>>>(t.Q, t.K, t.V, t.nvalid, S, t.O);
+    DYN_LAUNCH_CHECK();
+  }
+  RUN(run_lin(n, L.fc, L1(n, L.fc, t.O, t.O2, P, ACT_NONE), prec, st));
+  resid_ln_kernel<<<cdiv(P * 32, 256), 256, 0, st>>>(t.O2, t.G2, P_(n, L.ln_w), P_(n, L.ln_b), P, t.G3);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
 template <class Layout>
 static int run_trunk(const dyn_net* n, const Layout& L, const Seg& mv, const Seg& feat,
                      const float* weight1, const float* mask, long long M, long long P, int R,
@@ -550,31 +587,7 @@ static int run_trunk(const dyn_net* n, const Layout& L, const Seg& mv, const Seg
   DYN_LAUNCH_CHECK();
   mask_vis2_kernel<<<cdiv(M, 256), 256, 0, st>>>(t.vis2, mask, M);
   DYN_LAUNCH_CHECK();
-  // geometry_fc (:283 / :496)
-  RUN(run_lin(n, L.geo0, L1(n, L.geo0, t.G, t.GH, P, ACT_ELU), prec, st));
-  RUN(run_lin(n, L.geo2, L1(n, L.geo2, t.GH, t.G2, P, ACT_ELU), prec, st));
-  if (add_posenc) {
-    add_posenc_kernel<<<cdiv(P * 128, 256), 256, 0, st>>>(t.G2, P, S);
-    DYN_LAUNCH_CHECK();
-  }
-  // ray transformer (:287 / :500)
-  RUN(run_lin(n, L.wq, L1(n, L.wq, t.G2, t.Q, P, ACT_NONE), prec, st));
-  RUN(run_lin(n, L.wk, L1(n, L.wk, t.G2, t.K, P, ACT_NONE), prec, st));
-  RUN(run_lin(n, L.wv, L1(n, L.wv, t.G2, t.V, P, ACT_NONE), prec, st));
-  {
-    int threads = ((S + 31) / 32) * 32;
-    size_t smem = (size_t)2 * S * 33 * sizeof(float);
-    if (threads > 1024) return fail(DYN_E_INVALID, "ray transformer supports S <= 1024 (got %d)", S);
-    if (smem > 48 * 1024)
-      DYN_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-    attention_kernel<<<R, threads, smem, st>>>(t.Q, t.K, t.V, t.nvalid, S, t.O);
-    DYN_LAUNCH_CHECK();
-  }
-  RUN(run_lin(n, L.fc, L1(n, L.fc, t.O, t.O2, P, ACT_NONE), prec, st));
-  resid_ln_kernel<<<cdiv(P * 32, 256), 256, 0, st>>>(t.O2, t.G2, P_(n, L.ln_w), P_(n, L.ln_b), P, t.G3);
-  DYN_LAUNCH_CHECK();
-  return DYN_OK;
+  return run_point_tail(n, L, t.G, 257, P, R, S, add_posenc, t, prec, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -715,7 +728,7 @@ int net_static_f32(const dyn_net* n, const float* pts, const float* ref_rays, co
     RUN(run_lin(n, L.rgb0, a, prec, st));
     RUN(run_lin(n, L.rgb2, L1(n, L.rgb2, d.ch, d.ch2, M, ACT_ELU), prec, st));
     RUN(run_lin(n, L.rgb4, L1(n, L.rgb4, d.ch2, d.logit, M, ACT_NONE), prec, st));
-    st_out_kernel<<<cdiv(P, 256), 256, 0, st>>>(d.logit, d.meff, c_feat, d.sig, d.t.nvalid, P, V,
+    st_out_kernel<<<cdiv(P, 256), 256, 0, st>>>(d.logit, d.meff, c_feat, d.sig, d.t.nvalid, P, V, kF,
                                                 raw + p0 * 4);
     DYN_LAUNCH_CHECK();
   }
@@ -762,6 +775,138 @@ int motion_f32(const dyn_net* n, const float* x, int ldx, bool time_is_column, f
       float* t = cur; cur = nxt; nxt = t;
     }
     RUN(run_lin(n, L.coeff, L1(n, L.coeff, cur, coeff + i0 * L.coeff.out, N, ACT_NONE), prec, st));
+  }
+  return DYN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Fused (DYN_PREC_BF16) evaluation: per-view stage in ONE tcgen05 kernel
+// (nets_fused.cu: projection + gather + per-view MLP chain + pooling), then the
+// per-point tail and heads as staged tensor-core layers.
+// ---------------------------------------------------------------------------
+struct FusedBufs {
+  float *small, *refpl, *refpe, *reff, *G, *X, *vis2, *rd, *meff, *rgbin;
+  float *ptspe, *dirpe, *G4h, *G4, *sh, *sig, *ch, *ch2, *rgb, *logit;
+  TrunkBufs t;
+};
+
+static size_t fused_alloc(Bump& b, bool st_net, int R, int S, int V, FusedBufs* d) {
+  const long long P = (long long)R * S, M = P * V;
+  d->small = b.f(64);
+  d->G = b.f(P * kGStride);
+  trunk_alloc(b, 0, P, &d->t);
+  d->sh = b.f(P * 128); d->sig = b.f(P);
+  if (st_net) {
+    d->refpl = b.f((long long)R * 6); d->refpe = b.f((long long)R * 66); d->reff = b.f((long long)R * kF);
+    d->X = b.f(M * 128); d->vis2 = b.f(M); d->rd = b.f(M * 4); d->meff = b.f(M); d->rgbin = b.f(M * 3);
+    d->ch = b.f(M * 128); d->ch2 = b.f(M * 64); d->logit = b.f(M);
+  } else {
+    d->ptspe = b.f(P * 33); d->dirpe = b.f((long long)R * 27);
+    d->G4h = b.f(P * 256); d->G4 = b.f(P * 128);
+    d->ch = b.f(P * 128); d->ch2 = b.f(P * 64); d->rgb = b.f(P * 3);
+  }
+  return b.off;
+}
+
+size_t net_fused_workspace(int kind, int R, int S, int V) {
+  Bump b{nullptr, 0};
+  FusedBufs d;
+  int rc = net_rows_per_chunk(S, V);
+  return fused_alloc(b, kind == DYN_NET_STATIC, R < rc ? R : rc, S, V, &d);
+}
+
+static int fill_view_args(ViewFusedArgs* a, const float* query_cam, const float* src_rgbs,
+                          const float* src_cams, const float* feat_cl, int V, int S, int H, int W,
+                          int h, int w, cudaStream_t st) {
+  memset(a, 0, sizeof(*a));
+  RUN(build_view_cams(src_cams, V, query_cam, st, &a->cams));
+  a->h_img = a->cams.h_img; a->w_img = a->cams.w_img;
+  a->rgbs = src_rgbs; a->feat_cl = feat_cl;
+  a->H = H; a->W = W; a->h = h; a->w = w; a->V = V; a->S = S;
+  return DYN_OK;
+}
+
+int net_static_fused(const dyn_net* n, const float* pts, const float* ray_o, const float* ray_d,
+                     const float* query_cam, const float* src_rgbs, const float* src_cams,
+                     const float* feat_cl, int R_all, int S, int V, int H, int W, int h, int w,
+                     float* raw, float* mask_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const StaticLayout& L = n->sl;
+  const int prec = DYN_PREC_BF16;
+  ViewFusedArgs va;
+  RUN(fill_view_args(&va, query_cam, src_rgbs, src_cams, feat_cl, V, S, H, W, h, w, st));
+  const int RC = net_rows_per_chunk(S, V);
+  for (int r0 = 0; r0 < R_all; r0 += RC) {
+    const int R = (R_all - r0) < RC ? (R_all - r0) : RC;
+    const long long P = (long long)R * S, M = P * V, p0 = (long long)r0 * S;
+    Bump b{(char*)ws, 0};
+    FusedBufs d;
+    if (fused_alloc(b, true, R, S, V, &d) > ws_bytes)
+      return fail(DYN_E_WORKSPACE, "net_static_fused: workspace %zu < %zu", ws_bytes, b.off);
+    // per-ray reference feature: ref_feature_fc(PE(plucker(ray)))  (mlp_network.py:434,450)
+    RUN(dyn_plucker_ref(ray_o + (long long)r0 * 3, ray_d + (long long)r0 * 3, R, d.refpl, st));
+    RUN(launch_pe(d.refpl, 6, 6, 0, 0.f, 5, false, R, d.refpe, st));
+    RUN(launch_linear(L1(n, L.ref_feat, d.refpe, d.reff, R, ACT_NONE), st));
+    va.pts = pts + p0 * 3; va.pts_seq = nullptr; va.P = P;
+    va.ref_feat = d.reff; va.dfeat = nullptr;
+    va.G = d.G; va.nvalid = d.t.nvalid; va.mask_proj = mask_out + p0 * V; va.mask_eff = d.meff;
+    va.X = d.X; va.vis2 = d.vis2; va.ray_diff = d.rd; va.rgb_in = d.rgbin;
+    RUN(launch_view_fused(n, va, V, st));
+    RUN(run_point_tail(n, L, d.G, kGStride, P, R, S, /*add_posenc=*/false, d.t, prec, st));
+    RUN(run_lin(n, L.outgeo0, L1(n, L.outgeo0, d.t.G3, d.sh, P, ACT_ELU), prec, st));
+    RUN(run_lin(n, L.outgeo2, L1(n, L.outgeo2, d.sh, d.sig, P, ACT_NONE), prec, st));
+    LinArgs a = L1(n, L.rgb0, nullptr, d.ch, M, ACT_ELU);
+    a.seg[0] = Seg{d.t.G3, 128, 128, V}; a.seg[1] = Seg{d.X, 128, 128, 1};
+    a.seg[2] = Seg{d.vis2, 1, 1, 1}; a.seg[3] = Seg{d.rd, 4, 4, 1}; a.nseg = 4;
+    RUN(run_lin(n, L.rgb0, a, prec, st));
+    RUN(run_lin(n, L.rgb2, L1(n, L.rgb2, d.ch, d.ch2, M, ACT_ELU), prec, st));
+    RUN(run_lin(n, L.rgb4, L1(n, L.rgb4, d.ch2, d.logit, M, ACT_NONE), prec, st));
+    st_out_kernel<<<cdiv(P, 256), 256, 0, st>>>(d.logit, d.meff, d.rgbin, d.sig, d.t.nvalid, P, V, 3,
+                                                raw + p0 * 4);
+    DYN_LAUNCH_CHECK();
+  }
+  return DYN_OK;
+}
+
+int net_dynamic_fused(const dyn_net* n, const float* pts, const float* pts_seq, const float* ray_dir,
+                      const float* query_cam, const float* src_rgbs, const float* src_cams,
+                      const float* feat_cl, float time, int R_all, int S, int V, int H, int W, int h,
+                      int w, float* raw, float* mask_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const DynamicLayout& L = n->dl;
+  const int prec = DYN_PREC_BF16;
+  ViewFusedArgs va;
+  RUN(fill_view_args(&va, query_cam, src_rgbs, src_cams, feat_cl, V, S, H, W, h, w, st));
+  const long long P_all = (long long)R_all * S;
+  const int RC = net_rows_per_chunk(S, V);
+  for (int r0 = 0; r0 < R_all; r0 += RC) {
+    const int R = (R_all - r0) < RC ? (R_all - r0) : RC;
+    const long long P = (long long)R * S, p0 = (long long)r0 * S;
+    Bump b{(char*)ws, 0};
+    FusedBufs d;
+    if (fused_alloc(b, false, R, S, V, &d) > ws_bytes)
+      return fail(DYN_E_WORKSPACE, "net_dynamic_fused: workspace %zu < %zu", ws_bytes, b.off);
+    dyn_time_feat_kernel<<<1, 256, 0, st>>>(n->params, L, time, d.small);
+    DYN_LAUNCH_CHECK();
+    va.pts = pts + p0 * 3; va.pts_seq = pts_seq + p0 * 3; va.seq_stride = P_all; va.P = P;
+    va.ref_feat = nullptr; va.dfeat = d.small;
+    va.G = d.G; va.nvalid = d.t.nvalid; va.mask_proj = mask_out + p0 * V; va.mask_eff = nullptr;
+    va.X = nullptr; va.vis2 = nullptr; va.ray_diff = nullptr; va.rgb_in = nullptr;
+    RUN(launch_view_fused(n, va, V, st));
+    RUN(run_point_tail(n, L, d.G, kGStride, P, R, S, /*add_posenc=*/true, d.t, prec, st));
+    RUN(launch_pe(pts + p0 * 3, 3, 3, 0, 0.f, 5, false, P, d.ptspe, st));
+    LinArgs a = L1(n, L.refpts0, nullptr, d.G4h, P, ACT_ELU);
+    a.seg[0] = Seg{d.t.G3, 128, 128, 1}; a.seg[1] = Seg{d.ptspe, 33, 33, 1}; a.nseg = 2;
+    RUN(run_lin(n, L.refpts0, a, prec, st));
+    RUN(run_lin(n, L.refpts2, L1(n, L.refpts2, d.G4h, d.G4, P, ACT_ELU), prec, st));
+    RUN(run_lin(n, L.outgeo0, L1(n, L.outgeo0, d.G4, d.sh, P, ACT_ELU), prec, st));
+    RUN(run_lin(n, L.outgeo2, L1(n, L.outgeo2, d.sh, d.sig, P, ACT_NONE), prec, st));
+    RUN(launch_pe(ray_dir + (long long)r0 * 3, 3, 3, 0, 0.f, 4, false, R, d.dirpe, st));
+    a = L1(n, L.rgb0, nullptr, d.ch, P, ACT_ELU);
+    a.seg[0] = Seg{d.G4, 128, 128, 1}; a.seg[1] = Seg{d.dirpe, 27, 27, S}; a.nseg = 2;
+    RUN(run_lin(n, L.rgb0, a, prec, st));
+    RUN(run_lin(n, L.rgb2, L1(n, L.rgb2, d.ch, d.ch2, P, ACT_ELU), prec, st));
+    RUN(run_lin(n, L.rgb4, L1(n, L.rgb4, d.ch2, d.rgb, P, ACT_SIGMOID), prec, st));
+    dyn_out_kernel<<<cdiv(P, 256), 256, 0, st>>>(d.rgb, d.sig, d.t.nvalid, n->shift, P, raw + p0 * 4);
+    DYN_LAUNCH_CHECK();
   }
   return DYN_OK;
 }

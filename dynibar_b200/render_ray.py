@@ -24,6 +24,8 @@ from dynibar_b200.projection import project_gather
 # GEMM precision of the network kernels: _lib.PREC_FP32 (SIMT parity mode) or
 # _lib.PREC_BF16 (tcgen05, bf16 operands / fp32 accumulate).
 PRECISION = _lib.PREC_FP32
+# DYN_PREC_BF16: use the fused per-view kernels (False = staged tensor-core layers)
+USE_FUSED = True
 
 
 def set_precision(name):
@@ -205,6 +207,62 @@ def net_static_forward(module, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask
 
 
 # ---------------------------------------------------------------------------
+# fused a4-a11 (DYN_PREC_BF16): gather + per-view MLP chain in one tcgen05 kernel
+# ---------------------------------------------------------------------------
+def featmaps_channels_last(featmaps):
+  """[V,C,h,w] -> [V,h,w,C] on the device (one bilinear tap = 128 contiguous bytes)."""
+  V, Cc, h, w = featmaps.shape
+  dev = dev_of(featmaps)
+  out = torch.empty(V, h, w, Cc, device=dev)
+  A = Args()
+  with torch.cuda.device(dev):
+    check(lib.dyn_featmaps_channels_last(A(featmaps), ptr(out), V, Cc, h, w, stream()))
+  return out
+
+
+def net_static_fused(module, pts, ray_o, ray_d, query_cam, src_rgbs, src_cams, feat_cl):
+  """Projector.compute_with_motions + DynibarStatic.forward fused
+  (projection.py:103-176 + mlp_network.py:423-527) -> raw [R,S,4], mask [R,S,V,1]."""
+  dev = dev_of(pts)
+  net = _weights.packed_of(module, dev)
+  R, S = pts.shape[:2]
+  V = src_cams.shape[1]
+  _, _, H, W, _ = src_rgbs.shape
+  _, h, w, Cc = feat_cl.shape
+  raw = torch.empty(R, S, 4, device=dev)
+  mask = torch.empty(R, S, V, 1, device=dev)
+  nbytes = lib.dyn_net_fused_workspace_bytes(_lib.NET_STATIC, R, S, V)
+  ws = _lib.workspace.get(nbytes, dev)
+  A = Args()
+  with torch.cuda.device(dev):
+    check(lib.dyn_net_static_fused(net.handle, A(pts), A(ray_o), A(ray_d), A(query_cam), A(src_rgbs),
+                                   A(src_cams), A(feat_cl), R, S, V, H, W, Cc, h, w, ptr(raw),
+                                   ptr(mask), ws.data_ptr(), nbytes, stream()))
+  return raw, mask
+
+
+def net_dynamic_fused(module, pts, pts_seq, ray_dir, query_cam, src_rgbs, src_cams, feat_cl, time):
+  """Projector.compute_with_motions + DynibarDynamic.forward fused
+  (projection.py:103-176 + mlp_network.py:236-316) -> raw [R,S,4], mask [R,S,V,1]."""
+  dev = dev_of(pts)
+  net = _weights.packed_of(module, dev)
+  R, S = pts.shape[:2]
+  V = src_cams.shape[1]
+  _, _, H, W, _ = src_rgbs.shape
+  _, h, w, Cc = feat_cl.shape
+  raw = torch.empty(R, S, 4, device=dev)
+  mask = torch.empty(R, S, V, 1, device=dev)
+  nbytes = lib.dyn_net_fused_workspace_bytes(_lib.NET_DYNAMIC, R, S, V)
+  ws = _lib.workspace.get(nbytes, dev)
+  A = Args()
+  with torch.cuda.device(dev):
+    check(lib.dyn_net_dynamic_fused(net.handle, A(pts), A(pts_seq), A(ray_dir), A(query_cam),
+                                    A(src_rgbs), A(src_cams), A(feat_cl), float(time), R, S, V, H, W,
+                                    Cc, h, w, ptr(raw), ptr(mask), ws.data_ptr(), nbytes, stream()))
+  return raw, mask
+
+
+# ---------------------------------------------------------------------------
 # a12
 # ---------------------------------------------------------------------------
 def _composite(raw_dy, raw_st, z, mask_dy, V_dy, min_dy, mask_st, V_st, min_st):
@@ -311,14 +369,25 @@ def _render_pass(ray_batch, feat_dy, feat_st, pts, z, s, t, frame_idx, offsets, 
   ray_dir = ref_plucker[:, :3]  # == F.normalize(ray_d) (render_ray.py:455)
   coeff = motion_coefficients(motion, pts, t)
   seq = displaced_points(pts, coeff, basis, frame_idx, offsets, num_vv)
-  f_dy, _, m_dy = project_gather(pts, seq, cam, ray_batch["src_rgbs"], ray_batch["src_cameras"],
-                                 feat_dy)
-  f_st, rd_st, m_st = project_gather(pts, None, cam, ray_batch["static_src_rgbs"],
-                                     ray_batch["static_src_cameras"], feat_st)
-  raw_dy = net_dynamic_forward(net_dy, pts, f_dy, ray_dir, m_dy, t)
-  raw_st = net_static_forward(net_st, pts, ref_plucker,
-                              compute_src_plucker_coordinate(pts, ray_batch["static_src_cameras"]),
-                              f_st, rd_st, m_st)
+  fused = (PRECISION == _lib.PREC_BF16 and USE_FUSED and ray_batch["src_cameras"].shape[1] <= 16
+           and ray_batch["static_src_cameras"].shape[1] <= 16)
+  if fused:
+    # gather + per-view MLP chain + pooling in one tcgen05 kernel per branch: the
+    # [R,S,V,35] gather output and the per-view activations never reach HBM
+    raw_dy, m_dy = net_dynamic_fused(net_dy, pts, seq, ray_dir, cam, ray_batch["src_rgbs"],
+                                     ray_batch["src_cameras"], featmaps_channels_last(feat_dy), t)
+    raw_st, m_st = net_static_fused(net_st, pts, ray_o, ray_d, cam, ray_batch["static_src_rgbs"],
+                                    ray_batch["static_src_cameras"],
+                                    featmaps_channels_last(feat_st))
+  else:
+    f_dy, _, m_dy = project_gather(pts, seq, cam, ray_batch["src_rgbs"], ray_batch["src_cameras"],
+                                   feat_dy)
+    f_st, rd_st, m_st = project_gather(pts, None, cam, ray_batch["static_src_rgbs"],
+                                       ray_batch["static_src_cameras"], feat_st)
+    raw_dy = net_dynamic_forward(net_dy, pts, f_dy, ray_dir, m_dy, t)
+    raw_st = net_static_forward(net_st, pts, ref_plucker,
+                                compute_src_plucker_coordinate(pts, ray_batch["static_src_cameras"]),
+                                f_st, rd_st, m_st)
   V_dy, V_st = m_dy.shape[2], m_st.shape[2]
   # a sample counts when MORE THAN ONE view sees it (render_ray.py:524-529)
   out = _composite(raw_dy, raw_st, z, m_dy, V_dy, 1, m_st, V_st, 1)

@@ -141,6 +141,32 @@ int dyn_net_static(dyn_net_t net, const float* pts, const float* ref_rays,
                    int V, float* raw, void* workspace, size_t workspace_bytes,
                    int precision, void* stream);
 
+/* ---- fused a4-a11 (DYN_PREC_BF16): Projector.compute_with_motions fused INTO
+ * the network evaluation -- the [R,S,V,35] gather output never reaches HBM.
+ * Replaces the call pairs at render_ray.py:503-521 + :538-564 (== :715-774,
+ * :998-1059).  feat_cl is the CHANNELS-LAST copy [V,h,w,C] of the feature maps
+ * (dyn_featmaps_channels_last, once per frame).  mask_out [R,S,V] receives the
+ * projector mask (needed by dyn_composite).  V <= 16.
+ * static:  needs ray_o, ray_d [R,3] (Plucker coordinates are formed inside).
+ * dynamic: pts_seq [V,R,S,3] displaced points, ray_dir [R,3] normalised. */
+size_t dyn_net_fused_workspace_bytes(int kind, int R, int S, int V);
+int dyn_featmaps_channels_last(const float* featmaps, float* out, int V, int C,
+                               int h, int w, void* stream);
+int dyn_net_static_fused(dyn_net_t net, const float* pts, const float* ray_o,
+                         const float* ray_d, const float* query_cam,
+                         const float* src_rgbs, const float* src_cams,
+                         const float* feat_cl, int R, int S, int V, int H,
+                         int W, int C, int h, int w, float* raw,
+                         float* mask_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int dyn_net_dynamic_fused(dyn_net_t net, const float* pts, const float* pts_seq,
+                          const float* ray_dir, const float* query_cam,
+                          const float* src_rgbs, const float* src_cams,
+                          const float* feat_cl, float time, int R, int S, int V,
+                          int H, int W, int C, int h, int w, float* raw,
+                          float* mask_out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- a12: raw2outputs / raw2outputs_vanilla, render_ray.py:134-330 --------
  * raw_* [R,S,4]; z_vals [R,S]; mask_* [R,S,V*] as produced by
  * dyn_project_gather; a sample is "observed" when more than `min_views_*`

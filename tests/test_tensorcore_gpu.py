@@ -97,3 +97,37 @@ def test_bf16_mode_end_to_end(golden, name):
   assert_close_frac("weights", g["weights"], w["weights"], rtol=0, atol=2e-3, max_bad_frac=0.02)
   assert_close_frac("depth", g["depth"], w["depth"], rtol=2e-3, atol=1e-3, max_bad_frac=0.02)
   assert orc.psnr(g["rgb"].cpu(), w["rgb"]) > 50.0
+
+
+@pytest.mark.parametrize("name", ["mv_small", "mv_linear", "mono_small"])
+def test_fused_view_stage_matches_staged(golden, name):
+  """The fused per-view kernel (gather + MLP chain + pooling on tcgen05) against the
+  fp32 staged path on the same inputs: raw [R,S,4] of both nets and the projector mask."""
+  from dynibar_b200 import render_ray as rr
+  from dynibar_b200.projection import Projector
+  fx = golden(name)
+  cfg, st = fx["cfg"], fx["stages"]
+  batch, feat_c, feat_f, frame, t, offs, model, args = scenes.build(cfg)
+  d = lambda x: synthetic.to_device(x, DEV)
+  b, fc = d(batch), d(feat_c)
+  m = synthetic.model_to(model, DEV)
+  pts = d(st["pts"])
+  tt = float(t[0].float())
+  ray_dir = torch.nn.functional.normalize(b["ray_d"], dim=-1)
+  raw_st, m_st = rr.net_static_fused(m.net_coarse_st, pts, b["ray_o"], b["ray_d"], b["camera"],
+                                     b["static_src_rgbs"], b["static_src_cameras"],
+                                     rr.featmaps_channels_last(fc[2]))
+  raw_dy, m_dy = rr.net_dynamic_fused(m.net_coarse_dy, pts, d(st["seq"]), ray_dir, b["camera"],
+                                      b["src_rgbs"], b["src_cameras"],
+                                      rr.featmaps_channels_last(fc[0]), tt)
+  torch.cuda.synchronize()
+  assert_close_frac("mask_st", m_st, st["mask_st"], max_bad_frac=1e-3)
+  assert_close_frac("mask_dy", m_dy, st["mask_dy"], max_bad_frac=1e-3)
+  for br, raw in (("dy", raw_dy), ("st", raw_st)):
+    valid = (st["mask_" + br].sum(2) > 0)[..., 0]
+    got, want = raw.cpu(), st["raw_" + br]
+    assert (got[..., 3][~valid] == -1e9).all()
+    assert_close_frac("rgb_" + br, got[..., :3][valid], want[..., :3][valid], rtol=0, atol=1e-2,
+                      max_bad_frac=5e-3)
+    assert_close_frac("sigma_" + br, got[..., 3][valid], want[..., 3][valid], rtol=0, atol=2e-2,
+                      max_bad_frac=5e-3)
