@@ -127,32 +127,54 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const __grid_constant
     // fast path: one dense, 16-byte aligned fp32 source
     const bool dense = a.nseg == 1 && a.seg[0].div == 1 && (a.seg[0].ld & 3) == 0 &&
                        ((reinterpret_cast<uintptr_t>(a.seg[0].p) & 15) == 0);
+    const int lane = tid & 31;
     for (int kc = 0; kc < nchunks; ++kc) {
       const int ab = kc & 1;
-      float v[kKC];
       const int kbase = kc * kKC;
-      if (row_ok && dense && kbase + kKC <= a.K) {
-        const float4* src = reinterpret_cast<const float4*>(a.seg[0].p + row * a.seg[0].ld + kbase);
+      if (dense && kbase + kKC <= a.K) {
+        // coalesced: one warp instruction pair covers 4 rows x 64 floats (lane -> row l/8, k-group l%8)
+        float4 q0[8], q1[8];
+        float sc[8];
 #pragma unroll
-        for (int j = 0; j < kKC / 4; ++j) {
-          float4 q = __ldg(src + j);
-          v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        for (int rr = 0; rr < 8; ++rr) {
+          const int lr = warp * 32 + rr * 4 + (lane >> 3);
+          const long long grow = m0 + lr;
+          q0[rr] = make_float4(0.f, 0.f, 0.f, 0.f); q1[rr] = q0[rr]; sc[rr] = 1.f;
+          if (grow < a.M) {
+            const float4* src = reinterpret_cast<const float4*>(a.seg[0].p + grow * a.seg[0].ld + kbase + (lane & 7) * 8);
+            q0[rr] = __ldg(src); q1[rr] = __ldg(src + 1);
+            if (a.row_scale) sc[rr] = __ldg(a.row_scale + grow);
+          }
+        }
+        if (kc >= 2) mbar_wait(BAR(2 + ab), ((kc >> 1) - 1) & 1);
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int lr = warp * 32 + rr * 4 + (lane >> 3);
+          const int tl = lr >> 7, rl = lr & 127;
+          uint4 q;
+          q.x = pack_bf16x2(q0[rr].x * sc[rr], q0[rr].y * sc[rr]);
+          q.y = pack_bf16x2(q0[rr].z * sc[rr], q0[rr].w * sc[rr]);
+          q.z = pack_bf16x2(q1[rr].x * sc[rr], q1[rr].y * sc[rr]);
+          q.w = pack_bf16x2(q1[rr].z * sc[rr], q1[rr].w * sc[rr]);
+          *reinterpret_cast<uint4*>(a_buf + ab * kABufBytes + tl * kTileBytes + (lane & 7) * 2048 +
+                                    (rl >> 3) * 128 + (rl & 7) * 16) = q;
         }
       } else {
+        float v[kKC];
 #pragma unroll
         for (int j = 0; j < kKC; ++j)
           v[j] = (row_ok && kbase + j < a.K) ? seg_value(a, row, kbase + j) : 0.f;
-      }
-      if (kc >= 2) mbar_wait(BAR(2 + ab), ((kc >> 1) - 1) & 1);
-      uint8_t* dst = a_buf + ab * kABufBytes + tile * kTileBytes + (r >> 3) * 128 + (r & 7) * 16;
+        if (kc >= 2) mbar_wait(BAR(2 + ab), ((kc >> 1) - 1) & 1);
+        uint8_t* dst = a_buf + ab * kABufBytes + tile * kTileBytes + (r >> 3) * 128 + (r & 7) * 16;
 #pragma unroll
-      for (int g = 0; g < kKC / 8; ++g) {
-        uint4 q;
-        q.x = pack_bf16x2(v[8 * g + 0] * rs, v[8 * g + 1] * rs);
-        q.y = pack_bf16x2(v[8 * g + 2] * rs, v[8 * g + 3] * rs);
-        q.z = pack_bf16x2(v[8 * g + 4] * rs, v[8 * g + 5] * rs);
-        q.w = pack_bf16x2(v[8 * g + 6] * rs, v[8 * g + 7] * rs);
-        *reinterpret_cast<uint4*>(dst + g * (128 * 16)) = q;
+        for (int g = 0; g < kKC / 8; ++g) {
+          uint4 q;
+          q.x = pack_bf16x2(v[8 * g + 0] * rs, v[8 * g + 1] * rs);
+          q.y = pack_bf16x2(v[8 * g + 2] * rs, v[8 * g + 3] * rs);
+          q.z = pack_bf16x2(v[8 * g + 4] * rs, v[8 * g + 5] * rs);
+          q.w = pack_bf16x2(v[8 * g + 6] * rs, v[8 * g + 7] * rs);
+          *reinterpret_cast<uint4*>(dst + g * (128 * 16)) = q;
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(BAR(0 + ab));
@@ -161,20 +183,35 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const __grid_constant
     mbar_wait(BAR(10), 0);
     tc_fence_after_sync();
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32);
-    for (int cb = 0; cb < a.Npad; cb += 16) {
-      float acc[16];
-      tmem_ld16(tmem_addr(tmem_base, lane_base, (uint32_t)(tile * a.Npad + cb)), acc);
+    float* stg = reinterpret_cast<float*>(a_buf);  // [256][33] fp32 staging (33 KB of the 64 KB A area)
+    for (int cb = 0; cb < a.Npad; cb += 32) {
+      const int ncol = (a.Npad - cb) < 32 ? (a.Npad - cb) : 32;  // 32 or 16
+      float acc[32];
+      if (ncol == 32) {
+        tmem_ld32(tmem_addr(tmem_base, lane_base, (uint32_t)(tile * a.Npad + cb)), acc);
+      } else {
+        tmem_ld16(tmem_addr(tmem_base, lane_base, (uint32_t)(tile * a.Npad + cb)), acc);
+      }
       tmem_wait_ld();
-      if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = cb + i;
-          if (col < a.N) {
-            float y = act_f(acc[i] + (a.b ? a.b[col] : 0.f), a.act);
-            a.Y[row * a.ldy + col] = y;
-          }
+      for (int i = 0; i < 32; ++i) {
+        const int col = cb + i;
+        float y = 0.f;
+        if (i < ncol && col < a.N) y = act_f(acc[i] + (a.b ? __ldg(a.b + col) : 0.f), a.act);
+        stg[tid * 33 + i] = y;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      {
+        const int col = cb + lane;
+        const bool col_ok = lane < ncol && col < a.N;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          const int lr = warp * 32 + rr;
+          const long long grow = m0 + lr;
+          if (col_ok && grow < a.M) a.Y[grow * a.ldy + col] = stg[lr * 33 + lane];
         }
       }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     tc_fence_before_sync();
   }

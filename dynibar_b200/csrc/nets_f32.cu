@@ -319,9 +319,9 @@ __global__ void add_posenc_kernel(float* __restrict__ g, long long P, int S) {
 __global__ void attention_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                                  const float* __restrict__ Vv, const float* __restrict__ nvalid, int S,
                                  float* __restrict__ O) {
-  extern __shared__ float sm[];
-  float* Ks = sm;           // [S][33]
-  float* Vs = sm + S * 33;  // [S][33]
+  extern __shared__ __align__(16) float sm[];
+  float4* Ks = reinterpret_cast<float4*>(sm);          // [S][8] float4 = 32 floats per key
+  float4* Vs = reinterpret_cast<float4*>(sm) + S * 8;  // [S][8]
   const int ray = blockIdx.x;
   const int i = threadIdx.x;
   const long long base = (long long)ray * S;
@@ -329,36 +329,54 @@ __global__ void attention_kernel(const float* __restrict__ Q, const float* __res
   const float inv_temp = 1.f / sqrtf(32.f);
   for (int h = 0; h < 4; ++h) {
     __syncthreads();
-    for (int e = threadIdx.x; e < S * 32; e += blockDim.x) {
-      int j = e >> 5, d = e & 31;
-      Ks[j * 33 + d] = K[(base + j) * 128 + h * 32 + d];
-      Vs[j * 33 + d] = Vv[(base + j) * 128 + h * 32 + d];
+    for (int e = threadIdx.x; e < S * 8; e += blockDim.x) {
+      int j = e >> 3, d4 = e & 7;
+      Ks[e] = *reinterpret_cast<const float4*>(K + (base + j) * 128 + h * 32 + d4 * 4);
+      Vs[e] = *reinterpret_cast<const float4*>(Vv + (base + j) * 128 + h * 32 + d4 * 4);
     }
     __syncthreads();
     if (i < S) {
       float q[32], o[32];
 #pragma unroll
-      for (int d = 0; d < 32; ++d) {
-        q[d] = Q[(base + i) * 128 + h * 32 + d] * inv_temp;
-        o[d] = 0.f;
+      for (int d4 = 0; d4 < 8; ++d4) {
+        float4 t = *reinterpret_cast<const float4*>(Q + (base + i) * 128 + h * 32 + d4 * 4);
+        q[4 * d4] = t.x * inv_temp; q[4 * d4 + 1] = t.y * inv_temp;
+        q[4 * d4 + 2] = t.z * inv_temp; q[4 * d4 + 3] = t.w * inv_temp;
       }
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o[d] = 0.f;
       float mx = -INFINITY, den = 0.f;
       for (int j = 0; j < S; ++j) {
-        float l = 0.f;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-        for (int d = 0; d < 32; ++d) l = fmaf(q[d], Ks[j * 33 + d], l);
+        for (int d4 = 0; d4 < 8; ++d4) {
+          const float4 kk = Ks[j * 8 + d4];  // same address in every lane: broadcast
+          l0 = fmaf(q[4 * d4], kk.x, l0); l1 = fmaf(q[4 * d4 + 1], kk.y, l1);
+          l2 = fmaf(q[4 * d4 + 2], kk.z, l2); l3 = fmaf(q[4 * d4 + 3], kk.w, l3);
+        }
+        float l = (l0 + l1) + (l2 + l3);
         if (!row_ok) l = -1e9f;
-        float mn = fmaxf(mx, l);
-        float corr = expf(mx - mn);
-        float pj = expf(l - mn);
+        const float mn = fmaxf(mx, l);
+        const float corr = __expf(mx - mn);
+        const float pj = __expf(l - mn);
         den = den * corr + pj;
+        if (mn != mx) {  // rescale only when the running max moved
 #pragma unroll
-        for (int d = 0; d < 32; ++d) o[d] = o[d] * corr + pj * Vs[j * 33 + d];
+          for (int d = 0; d < 32; ++d) o[d] *= corr;
+        }
+#pragma unroll
+        for (int d4 = 0; d4 < 8; ++d4) {
+          const float4 vv = Vs[j * 8 + d4];
+          o[4 * d4] = fmaf(pj, vv.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(pj, vv.y, o[4 * d4 + 1]);
+          o[4 * d4 + 2] = fmaf(pj, vv.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, vv.w, o[4 * d4 + 3]);
+        }
         mx = mn;
       }
-      float inv = 1.f / den;
+      const float inv = 1.f / den;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) O[(base + i) * 128 + h * 32 + d] = o[d] * inv;
+      for (int d4 = 0; d4 < 8; ++d4)
+        *reinterpret_cast<float4*>(O + (base + i) * 128 + h * 32 + d4 * 4) =
+            make_float4(o[4 * d4] * inv, o[4 * d4 + 1] * inv, o[4 * d4 + 2] * inv, o[4 * d4 + 3] * inv);
     }
   }
 }
@@ -508,7 +526,7 @@ static LinArgs L1(const dyn_net* n, const LinearP& l, const float* X, float* Y, 
   } while (0)
 
 int net_rows_per_chunk(int S, int V) {
-  long long rows = 524288;
+  long long rows = 4194304;  // (point, view) rows per internal chunk (workspace ~1.5 KB/row)
   long long r = rows / ((long long)S * V);
   return (int)(r < 1 ? 1 : r);
 }
@@ -548,7 +566,7 @@ static int run_point_tail(const dyn_net* n, const Layout& L, const float* G, int
   RUN(run_lin(n, L.wv, L1(n, L.wv, t.G2, t.V, P, ACT_NONE), prec, st));
   {
     int threads = ((S + 31) / 32) * 32;
-    size_t smem = (size_t)2 * S * 33 * sizeof(float);
+    size_t smem = (size_t)2 * S * 32 * sizeof(float);
     if (threads > 1024) return fail(DYN_E_INVALID, "ray transformer supports S <= 1024 (got %d)", S);
     if (smem > 48 * 1024)
       DYN_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
