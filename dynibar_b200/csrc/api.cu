@@ -57,9 +57,9 @@ size_t dyn_net_param_count(int kind) {
 
 size_t dyn_net_packed_bytes(int kind) {
   switch (kind) {
-    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes + fused_view_bytes(kind);
-    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes + fused_view_bytes(kind);
-    case DYN_NET_MOTION: return (size_t)motion_layout(8).all.packed_bytes;
+    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes + fused_view_bytes(kind) + fused_chain_bytes(kind);
+    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes + fused_view_bytes(kind) + fused_chain_bytes(kind);
+    case DYN_NET_MOTION: return (size_t)motion_layout(8).all.packed_bytes + fused_chain_bytes(kind);
     default: return 0;
   }
 }
@@ -113,15 +113,19 @@ int dyn_net_create(int kind, const float* params, size_t n_params, void* packed,
                               reinterpret_cast<char*>(packed) + ll.l[i].tc, (cudaStream_t)stream);
       if (rc) { free(n); return rc; }
     }
-    if (kind != DYN_NET_MOTION) {  // fused per-view images: packed on the host once
+    {  // fused tensor-core images (per-view stage, row-local chains): packed on the host once
       float* hp = (float*)malloc(n_params * sizeof(float));
       if (!hp) { free(n); return fail(DYN_E_INVALID, "out of host memory"); }
       cudaError_t e = cudaMemcpyAsync(hp, params, n_params * sizeof(float), cudaMemcpyDeviceToHost,
                                       (cudaStream_t)stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
-      int rc = e == cudaSuccess ? fused_view_build(n, hp, reinterpret_cast<char*>(packed) + ll.packed_bytes,
-                                                   fused_view_bytes(kind), (cudaStream_t)stream)
-                                : fail(DYN_E_CUDA, "reading parameters back: %s", cudaGetErrorString(e));
+      int rc = e == cudaSuccess ? DYN_OK : fail(DYN_E_CUDA, "reading parameters back: %s", cudaGetErrorString(e));
+      char* cur = reinterpret_cast<char*>(packed) + ll.packed_bytes;
+      if (!rc && kind != DYN_NET_MOTION) {
+        rc = fused_view_build(n, hp, cur, fused_view_bytes(kind), (cudaStream_t)stream);
+        cur += fused_view_bytes(kind);
+      }
+      if (!rc) rc = fused_chain_build(n, hp, cur, fused_chain_bytes(kind), (cudaStream_t)stream);
       free(hp);
       if (rc) { free(n); return rc; }
     }
@@ -175,6 +179,14 @@ int dyn_net_dynamic_fused(dyn_net_t net, const float* pts, const float* pts_seq,
   if (R == 0) return DYN_OK;
   return net_dynamic_fused(net, pts, pts_seq, ray_dir, query_cam, src_rgbs, src_cams, feat_cl, time, R, S,
                            V, H, W, h, w, raw, mask_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dyn_debug_point_chain(dyn_net_t net, const float* G, const float* nvalid, const float* pts,
+                          const float* ray_dir, int R, int S, float* g2, float* Q, float* K, float* V,
+                          float* O, float* out_a, float* out_b, float* posenc_ws, void* stream) {
+  DYN_CHECK_ARG(net && G && nvalid && g2 && Q && K && V && O && out_a && posenc_ws);
+  return debug_point_chain(net, G, nvalid, pts, ray_dir, R, S, g2, Q, K, V, O, out_a, out_b, posenc_ws,
+                           (cudaStream_t)stream);
 }
 
 int dyn_motion_coeffs(dyn_net_t motion, const float* pts, float time, int R, int S, float* coeff,

@@ -86,6 +86,13 @@ DynamicLayout dynamic_layout();
 StaticLayout static_layout(bool anti_alias);
 MotionLayout motion_layout(int nb);
 
+struct FusedChunk;
+struct ChainImage {
+  const void* img;
+  const FusedChunk* tab;
+  int nchunks;
+};
+
 }  // namespace dyn
 
 struct dyn_net {
@@ -104,6 +111,9 @@ struct dyn_net {
   void* fused_img;
   void* fused_tab;
   int fused_nchunks;
+  // row-local fused chains (chains_fused.cu): motion: [0]; aggregation nets:
+  // [0] point stage 1, [1] point stage 2, [2] static blending head
+  dyn::ChainImage chain[3];
 };
 
 // ---- device helpers ---------------------------------------------------------

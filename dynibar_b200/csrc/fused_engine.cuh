@@ -1,0 +1,228 @@
+// Shared machinery of the fused tcgen05 kernels (nets_fused.cu, chains_fused.cu):
+// smem budget constants, fast activations, A-tile stores, view-group shuffles,
+// the table-driven weight producer and MMA issuer, and the host-side packing of
+// weight chunks into UMMA images.
+#pragma once
+#include <vector>
+
+#include "nets_fused.cuh"
+#include "tc.cuh"
+
+namespace dyn {
+namespace fe {
+
+using namespace tc;
+
+constexpr int kRing = 4;
+constexpr int kStageBytes = 16384;
+constexpr int kATileBytes = 69632;  // 128 rows x 272 cols bf16 (34 k-groups: geometry_fc.0 has K = 257)
+constexpr int kConstFloats = 2048;
+constexpr int kSmemFused = 2 * kATileBytes + kRing * kStageBytes + kConstFloats * 4 + 256;
+// barrier slots inside the fused kernels: [0..3] w_full, [4..7] w_empty, [8] a_ready, [9] acc_full
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float elu_fast(float x) {
+  float e = ex2f(x * 1.4426950408889634f);
+  return x > 0.f ? x : e - 1.f;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  return __frcp_rn(1.f + ex2f(-x * 1.4426950408889634f));
+}
+
+// 8 consecutive columns [c0, c0+8) of this thread's row -> one 16-byte store
+__device__ __forceinline__ void store8(uint8_t* arow, int c0, const float* v) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(arow + (c0 >> 3) * 2048) = q;
+}
+
+// acc[32] (+bias, ELU) -> bf16 columns [c0, c0+32) of the A tile, optional row scale
+template <bool kElu>
+__device__ __forceinline__ void epi32_to_A(uint8_t* arow, int c0, float* acc, const float* bias,
+                                           float scale) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float v = acc[i] + bias[c0 + i];
+    if (kElu) v = elu_fast(v);
+    acc[i] = v * scale;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) store8(arow, c0 + 8 * g, acc + 8 * g);
+}
+
+// PE with frequencies 2^k via angle doubling: out = [x(D), cos(2^k x)(NF*D), sin(2^k x)(NF*D)]
+template <int D, int NF>
+__device__ __forceinline__ void pe_pow2(const float* x, float* out) {
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    out[d] = x[d];
+    float s, c;
+    __sincosf(x[d], &s, &c);
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+      out[D + k * D + d] = c;
+      out[D + NF * D + k * D + d] = s;
+      float s2 = 2.f * s * c, c2 = 1.f - 2.f * s * s;
+      s = s2; c = c2;
+    }
+  }
+}
+
+template <int VP>
+__device__ __forceinline__ float group_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  if (VP == 16) v += __shfl_xor_sync(0xffffffffu, v, 8);
+  return v;
+}
+template <int VP>
+__device__ __forceinline__ float group_min(float v) {
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  if (VP == 16) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  return v;
+}
+
+// one reduce-scatter step over N values: lanes with `bit` set keep the upper half
+template <int N>
+__device__ __forceinline__ void rs_step(const float* in, float* out, bool upper, int xr) {
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    float send = upper ? in[i] : in[N / 2 + i];
+    float keep = upper ? in[N / 2 + i] : in[i];
+    out[i] = keep + __shfl_xor_sync(0xffffffffu, send, xr);
+  }
+}
+
+
+// ---- control warps (one elected lane each) -------------------------------------
+// weight producer: streams the chunk table once per iteration through the ring
+__device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chunks, int nchunks,
+                                              const void* wimg, int n_iter, uint8_t* ring, uint32_t bar0) {
+  const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(wimg);
+  uint32_t cnt = 0;
+  for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
+    for (int c = 0; c < nchunks; ++c, ++cnt) {
+      const uint32_t st = cnt % kRing;
+      if (cnt >= kRing) mbar_wait(bar0 + 8u * (4 + st), ((cnt / kRing) - 1) & 1);
+      const FusedChunk ch = chunks[c];
+      mbar_arrive_expect_tx(bar0 + 8u * st, ch.bytes);
+      bulk_g2s(smem_u32(ring + st * kStageBytes), wsrc + ch.off, ch.bytes, bar0 + 8u * st);
+    }
+  }
+}
+
+// MMA issuer: per chunk, both 128-row tiles consume the same weight stage.
+// FusedChunk.flags: 1 = wait for a_ready before this chunk, 2 = last chunk of a
+// round (commit acc_full), 8 = first k-step overwrites D (start of a layer);
+// d_col = accumulator column offset inside the tile's 256-column TMEM region.
+__device__ __forceinline__ void issuer_loop(const FusedChunk* __restrict__ chunks, int nchunks, int n_iter,
+                                            uint8_t* smem, uint8_t* ring, uint32_t bar0,
+                                            uint32_t tmem_base) {
+  uint32_t cnt = 0, a_cnt = 0;
+  const uint32_t a_addr0 = smem_u32(smem), a_addr1 = smem_u32(smem + kATileBytes);
+  for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
+    for (int c = 0; c < nchunks; ++c, ++cnt) {
+      const FusedChunk ch = chunks[c];
+      if (ch.flags & 1) {
+        mbar_wait(bar0 + 8u * 8, a_cnt & 1);
+        ++a_cnt;
+        tc_fence_after_sync();
+      }
+      const uint32_t st = cnt % kRing;
+      mbar_wait(bar0 + 8u * st, (cnt / kRing) & 1);
+      tc_fence_after_sync();
+      const uint32_t idesc = idesc_bf16_f32(128, ch.npad);
+      const uint32_t w_addr = smem_u32(ring + st * kStageBytes);
+      const uint32_t lbo_b = (uint32_t)ch.npad * 16u;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t aa = (t ? a_addr1 : a_addr0) + (uint32_t)ch.a_kgroup * 2048u;
+        for (int ks = 0; ks < ch.ksteps; ++ks) {
+          mma_bf16_ss(tmem_base + t * 256 + ch.d_col, smem_desc(aa + ks * 4096u, 2048u, 128u),
+                      smem_desc(w_addr + ks * 2u * lbo_b, lbo_b, 128u), idesc,
+                      ((ch.flags & 8) && ks == 0) ? 0u : 1u);
+        }
+      }
+      mma_commit(bar0 + 8u * (4 + st));
+      if (ch.flags & 2) mma_commit(bar0 + 8u * 9);
+    }
+  }
+}
+
+// ---- host side: weight images + chunk table ------------------------------------
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;  // round to nearest even
+  return (uint16_t)(u >> 16);
+}
+
+struct HostLayer {
+  const float* W;  // host fp32 [*, Kw]
+  int N, Kw, Npad, Kpad;
+  std::vector<int> colmap;  // size Kpad: weight column or -1
+};
+
+inline void append_layer(const HostLayer& L, std::vector<uint8_t>& img, std::vector<FusedChunk>& tab,
+                         int d_col = 0, int a_kgroup0 = 0, int first_flags = 9, bool last = true) {
+  int steps_per_chunk = kStageBytes / (L.Npad * 32);
+  if (steps_per_chunk > 8) steps_per_chunk = 8;
+  const int ksteps_total = L.Kpad / 16;
+  for (int k0 = 0; k0 < ksteps_total; k0 += steps_per_chunk) {
+    const int ks = (ksteps_total - k0) < steps_per_chunk ? (ksteps_total - k0) : steps_per_chunk;
+    FusedChunk ch;
+    ch.off = (uint32_t)img.size();
+    ch.bytes = (uint32_t)(L.Npad * 32 * ks);
+    ch.npad = (uint16_t)L.Npad;
+    ch.ksteps = (uint8_t)ks;
+    ch.flags = (uint8_t)((k0 == 0 ? first_flags : 0) | ((last && k0 + ks >= ksteps_total) ? 2 : 0));
+    ch.a_kgroup = (uint16_t)(a_kgroup0 + k0 * 2);
+    ch.d_col = (uint16_t)d_col;
+    img.resize(img.size() + ch.bytes, 0);
+    uint16_t* dst = reinterpret_cast<uint16_t*>(img.data() + ch.off);
+    for (int n = 0; n < L.Npad; ++n)
+      for (int kk = 0; kk < ks * 16; ++kk) {
+        const int col = L.colmap[k0 * 16 + kk];
+        const float val = (n < L.N && col >= 0) ? L.W[(size_t)n * L.Kw + col] : 0.f;
+        dst[tile_off((uint32_t)L.Npad, (uint32_t)n, (uint32_t)kk) / 2] = f2bf(val);
+      }
+    tab.push_back(ch);
+  }
+}
+
+inline std::vector<int> identity_map(int K, int Kpad) {
+  std::vector<int> m(Kpad, -1);
+  for (int i = 0; i < K; ++i) m[i] = i;
+  return m;
+}
+// [mean8 | var8 | feat8] per channel group; C channels, source columns
+// [0,C) mean, [C,2C) var, [2C,3C) per-view feature
+inline std::vector<int> pooled_map(int C, int groups, int Kpad) {
+  std::vector<int> m(Kpad, -1);
+  for (int g = 0; g < groups; ++g)
+    for (int j = 0; j < 8; ++j) {
+      const int c = 8 * g + j;
+      if (c < C) {
+        m[24 * g + j] = c;
+        m[24 * g + 8 + j] = C + c;
+        m[24 * g + 16 + j] = 2 * C + c;
+      }
+    }
+  return m;
+}
+
+
+}  // namespace fe
+}  // namespace dyn

@@ -28,6 +28,9 @@ int net_dynamic_fused(const dyn_net* n, const float* pts, const float* pts_seq, 
                       const float* query_cam, const float* src_rgbs, const float* src_cams,
                       const float* feat_cl, float time, int R, int S, int V, int H, int W, int h, int w,
                       float* raw, float* mask_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int debug_point_chain(const dyn_net* n, const float* G, const float* nvalid, const float* pts,
+                      const float* ray_dir, int R, int S, float* g2, float* Q, float* K, float* V,
+                      float* O, float* out_a, float* out_b, float* posenc_ws, cudaStream_t st);
 int zero_last_samples(float* coeff, int R, int S, int width, cudaStream_t st);
 
 }  // namespace dyn

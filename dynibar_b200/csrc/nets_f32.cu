@@ -310,6 +310,15 @@ __global__ void add_posenc_kernel(float* __restrict__ g, long long P, int S) {
   g[idx] += (float)((j & 1) ? cos(ang) : sin(ang));
 }
 
+// sinusoid table [S,128] (mlp_network.py:220-234), double precision like numpy
+__global__ void posenc_table_kernel(float* __restrict__ tab, int S) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * 128) return;
+  int s = idx >> 7, j = idx & 127;
+  double ang = (double)s / pow(10000.0, 2.0 * (double)(j / 2) / 128.0);
+  tab[idx] = (float)((j & 1) ? cos(ang) : sin(ang));
+}
+
 // ---------------------------------------------------------------------------
 // a11 ray transformer core: softmax(q k^T / sqrt(dk)) v per ray and head.
 // Block per ray, thread per query sample, K/V of one head staged in smem.
@@ -769,6 +778,14 @@ size_t motion_f32_workspace(long long N) {
 int motion_f32(const dyn_net* n, const float* x, int ldx, bool time_is_column, float time,
                long long N_all, float* coeff, void* ws, size_t ws_bytes, int prec, cudaStream_t st) {
   const MotionLayout& L = n->ml;
+  if (prec == DYN_PREC_BF16 && n->chain[0].img != nullptr) {
+    // whole MLP in one tcgen05 kernel (chains_fused.cu); no workspace needed
+    MotionFusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.ldx = ldx; a.time_is_column = time_is_column ? 1 : 0; a.time = time;
+    a.N = N_all; a.S = 0; a.n_last = 0; a.coeff = coeff;
+    return launch_motion_fused(n, a, st);
+  }
   for (long long i0 = 0; i0 < N_all; i0 += kMotionRows) {
     long long N = (N_all - i0) < kMotionRows ? (N_all - i0) : kMotionRows;
     Bump b{(char*)ws, 0};
@@ -833,6 +850,49 @@ size_t net_fused_workspace(int kind, int R, int S, int V) {
   return fused_alloc(b, kind == DYN_NET_STATIC, R < rc ? R : rc, S, V, &d);
 }
 
+// per-point stage on the fused chains: point1 (geometry_fc, Q|K|V) -> ray-transformer
+// attention (SIMT fp32) -> point2 (fc + LayerNorm + heads)
+static int run_point_fused(const dyn_net* n, const float* G, long long P, int R, int S, bool dynamic,
+                           float* posenc_tab, TrunkBufs& t, Point2Args& p2, cudaStream_t st) {
+  Point1Args p1;
+  memset(&p1, 0, sizeof(p1));
+  p1.G = G; p1.P = P; p1.S = S; p1.g2 = t.G2; p1.Q = t.Q; p1.K = t.K; p1.V = t.V;
+  p1.posenc = nullptr;
+  if (dynamic) {
+    posenc_table_kernel<<<cdiv((long long)S * 128, 256), 256, 0, st>>>(posenc_tab, S);
+    DYN_LAUNCH_CHECK();
+    p1.posenc = posenc_tab;
+  }
+  RUN(launch_point1_fused(n, p1, st));
+  {
+    int threads = ((S + 31) / 32) * 32;
+    size_t smem = (size_t)2 * S * 32 * sizeof(float);
+    if (threads > 1024) return fail(DYN_E_INVALID, "ray transformer supports S <= 1024 (got %d)", S);
+    if (smem > 48 * 1024)
+      DYN_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    attention_kernel<<<R, threads, smem, st>>>(t.Q, t.K, t.V, t.nvalid, S, t.O);
+    DYN_LAUNCH_CHECK();
+  }
+  p2.O = t.O; p2.g2 = t.G2; p2.nvalid = t.nvalid; p2.P = P; p2.S = S;
+  return launch_point2_fused(n, p2, st);
+}
+
+// unit-test hook: the per-point fused stage on caller-provided G / nvalid
+int debug_point_chain(const dyn_net* n, const float* G, const float* nvalid, const float* pts,
+                      const float* ray_dir, int R, int S, float* g2, float* Q, float* K, float* V,
+                      float* O, float* out_a, float* out_b, float* posenc_ws, cudaStream_t st) {
+  TrunkBufs t;
+  memset(&t, 0, sizeof(t));
+  t.G2 = g2; t.Q = Q; t.K = K; t.V = V; t.O = O; t.nvalid = const_cast<float*>(nvalid);
+  Point2Args p2;
+  memset(&p2, 0, sizeof(p2));
+  const bool dynamic = n->kind == DYN_NET_DYNAMIC;
+  if (dynamic) { p2.pts = pts; p2.ray_dir = ray_dir; p2.raw = out_a; }
+  else { p2.GW = out_a; p2.sigma = out_b; }
+  return run_point_fused(n, G, (long long)R * S, R, S, dynamic, posenc_ws, t, p2, st);
+}
+
 static int fill_view_args(ViewFusedArgs* a, const float* query_cam, const float* src_rgbs,
                           const float* src_cams, const float* feat_cl, int V, int S, int H, int W,
                           int h, int w, cudaStream_t st) {
@@ -869,18 +929,19 @@ int net_static_fused(const dyn_net* n, const float* pts, const float* ray_o, con
     va.G = d.G; va.nvalid = d.t.nvalid; va.mask_proj = mask_out + p0 * V; va.mask_eff = d.meff;
     va.X = d.X; va.vis2 = d.vis2; va.ray_diff = d.rd; va.rgb_in = d.rgbin;
     RUN(launch_view_fused(n, va, V, st));
-    RUN(run_point_tail(n, L, d.G, kGStride, P, R, S, /*add_posenc=*/false, d.t, prec, st));
-    RUN(run_lin(n, L.outgeo0, L1(n, L.outgeo0, d.t.G3, d.sh, P, ACT_ELU), prec, st));
-    RUN(run_lin(n, L.outgeo2, L1(n, L.outgeo2, d.sh, d.sig, P, ACT_NONE), prec, st));
-    LinArgs a = L1(n, L.rgb0, nullptr, d.ch, M, ACT_ELU);
-    a.seg[0] = Seg{d.t.G3, 128, 128, V}; a.seg[1] = Seg{d.X, 128, 128, 1};
-    a.seg[2] = Seg{d.vis2, 1, 1, 1}; a.seg[3] = Seg{d.rd, 4, 4, 1}; a.nseg = 4;
-    RUN(run_lin(n, L.rgb0, a, prec, st));
-    RUN(run_lin(n, L.rgb2, L1(n, L.rgb2, d.ch, d.ch2, M, ACT_ELU), prec, st));
-    RUN(run_lin(n, L.rgb4, L1(n, L.rgb4, d.ch2, d.logit, M, ACT_NONE), prec, st));
-    st_out_kernel<<<cdiv(P, 256), 256, 0, st>>>(d.logit, d.meff, d.rgbin, d.sig, d.t.nvalid, P, V, 3,
-                                                raw + p0 * 4);
-    DYN_LAUNCH_CHECK();
+    {
+      Point2Args p2;
+      memset(&p2, 0, sizeof(p2));
+      p2.GW = d.ch;  // [P,128] (the staged head's scratch is free on this path)
+      p2.sigma = d.sig;
+      RUN(run_point_fused(n, d.G, P, R, S, false, nullptr, d.t, p2, st));
+      RgbHeadArgs rh;
+      memset(&rh, 0, sizeof(rh));
+      rh.X = d.X; rh.vis2 = d.vis2; rh.ray_diff = d.rd; rh.mask_eff = d.meff; rh.rgb_in = d.rgbin;
+      rh.GW = d.ch; rh.sigma = d.sig; rh.P = P; rh.V = V; rh.raw = raw + p0 * 4;
+      RUN(launch_rgbhead_fused(n, rh, st));
+    }
+    (void)prec; (void)M;
   }
   return DYN_OK;
 }
@@ -909,22 +970,13 @@ int net_dynamic_fused(const dyn_net* n, const float* pts, const float* pts_seq, 
     va.G = d.G; va.nvalid = d.t.nvalid; va.mask_proj = mask_out + p0 * V; va.mask_eff = nullptr;
     va.X = nullptr; va.vis2 = nullptr; va.ray_diff = nullptr; va.rgb_in = nullptr;
     RUN(launch_view_fused(n, va, V, st));
-    RUN(run_point_tail(n, L, d.G, kGStride, P, R, S, /*add_posenc=*/true, d.t, prec, st));
-    RUN(launch_pe(pts + p0 * 3, 3, 3, 0, 0.f, 5, false, P, d.ptspe, st));
-    LinArgs a = L1(n, L.refpts0, nullptr, d.G4h, P, ACT_ELU);
-    a.seg[0] = Seg{d.t.G3, 128, 128, 1}; a.seg[1] = Seg{d.ptspe, 33, 33, 1}; a.nseg = 2;
-    RUN(run_lin(n, L.refpts0, a, prec, st));
-    RUN(run_lin(n, L.refpts2, L1(n, L.refpts2, d.G4h, d.G4, P, ACT_ELU), prec, st));
-    RUN(run_lin(n, L.outgeo0, L1(n, L.outgeo0, d.G4, d.sh, P, ACT_ELU), prec, st));
-    RUN(run_lin(n, L.outgeo2, L1(n, L.outgeo2, d.sh, d.sig, P, ACT_NONE), prec, st));
-    RUN(launch_pe(ray_dir + (long long)r0 * 3, 3, 3, 0, 0.f, 4, false, R, d.dirpe, st));
-    a = L1(n, L.rgb0, nullptr, d.ch, P, ACT_ELU);
-    a.seg[0] = Seg{d.G4, 128, 128, 1}; a.seg[1] = Seg{d.dirpe, 27, 27, S}; a.nseg = 2;
-    RUN(run_lin(n, L.rgb0, a, prec, st));
-    RUN(run_lin(n, L.rgb2, L1(n, L.rgb2, d.ch, d.ch2, P, ACT_ELU), prec, st));
-    RUN(run_lin(n, L.rgb4, L1(n, L.rgb4, d.ch2, d.rgb, P, ACT_SIGMOID), prec, st));
-    dyn_out_kernel<<<cdiv(P, 256), 256, 0, st>>>(d.rgb, d.sig, d.t.nvalid, n->shift, P, raw + p0 * 4);
-    DYN_LAUNCH_CHECK();
+    {
+      Point2Args p2;
+      memset(&p2, 0, sizeof(p2));
+      p2.pts = pts + p0 * 3; p2.ray_dir = ray_dir + (long long)r0 * 3; p2.raw = raw + p0 * 4;
+      RUN(run_point_fused(n, d.G, P, R, S, true, d.G4h, d.t, p2, st));
+    }
+    (void)prec;
   }
   return DYN_OK;
 }

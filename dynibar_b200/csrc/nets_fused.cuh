@@ -10,10 +10,11 @@ struct FusedChunk {
   uint32_t off, bytes;   // weight chunk inside the image
   uint16_t npad;         // UMMA N of the layer
   uint8_t ksteps;        // K = 16 * ksteps in this chunk
-  uint8_t flags;         // 1: first chunk of a layer (wait for the operand, overwrite D)
-                         // 2: last chunk of a layer (signal the epilogue)
+  uint8_t flags;         // 1: wait for the operand (a_ready) before this chunk
+                         // 2: last chunk of a round (signal the epilogue)
+                         // 8: first k-step overwrites D (start of a layer)
   uint16_t a_kgroup;     // first 8-column group of the A tile this chunk consumes
-  uint16_t pad;
+  uint16_t d_col;        // accumulator column offset inside the tile's TMEM region
 };
 
 struct ViewFusedArgs {
@@ -45,6 +46,75 @@ struct ViewFusedArgs {
   float* ray_diff;   // static [P*V,4]
   float* rgb_in;     // static [P*V,3] gathered source colours
 };
+
+// ---- row-local fused chains (chains_fused.cu) ----
+struct MotionFusedArgs {
+  const float* x;  // [N, ldx] xyz (+ time column when time_is_column)
+  int ldx, time_is_column;
+  float time;
+  long long N;
+  int S, n_last;   // zero the last n_last samples of each S-sample ray (S = 0: never)
+  float* coeff;    // [N, ncoef]
+  int ncoef;
+  const float* params;
+  int o_bias[9];
+  const void* wimg;
+  const FusedChunk* chunks;
+  int nchunks;
+};
+
+struct Point1Args {
+  const float* G;       // [P, kGStride]
+  const float* posenc;  // [S,128] sinusoid table (dynamic) or null
+  long long P;
+  int S;
+  float *g2, *Q, *K, *V;  // [P,128] each
+  const float* params;
+  int o_bgeo0, o_bgeo2;
+  const void* wimg;
+  const FusedChunk* chunks;
+  int nchunks;
+};
+
+struct Point2Args {
+  const float* O;       // [P,128] attention output
+  const float* g2;      // [P,128] residual
+  const float* nvalid;  // [P]
+  const float* pts;     // [P,3]   (dynamic)
+  const float* ray_dir; // [R,3]   (dynamic)
+  long long P;
+  int S;
+  float shift;
+  float* raw;    // dynamic: [P,4]
+  float* GW;     // static:  [P,128] per-point part of rgb_fc.0 (bias included)
+  float* sigma;  // static:  [P] masked density
+  const float* params;
+  int o_lnw, o_lnb, o_brefpts0, o_brefpts2, o_boutgeo0, o_woutgeo2, o_boutgeo2, o_brgb0, o_brgb2,
+      o_wrgb4, o_brgb4;
+  const void* wimg;
+  const FusedChunk* chunks;
+  int nchunks;
+};
+
+struct RgbHeadArgs {
+  const float *X, *vis2, *ray_diff, *mask_eff, *rgb_in, *GW, *sigma;
+  long long P;
+  int V;
+  float* raw;  // [P,4]
+  const float* params;
+  int o_brgb2, o_wrgb4, o_brgb4;
+  const void* wimg;
+  const FusedChunk* chunks;
+  int nchunks;
+};
+
+size_t fused_chain_bytes(int kind);
+int fused_chain_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes,
+                      cudaStream_t st);
+int launch_motion_fused(const dyn_net* n, MotionFusedArgs& a, cudaStream_t st);
+int launch_point1_fused(const dyn_net* n, Point1Args& a, cudaStream_t st);
+int launch_point2_fused(const dyn_net* n, Point2Args& a, cudaStream_t st);
+int launch_rgbhead_fused(const dyn_net* n, RgbHeadArgs& a, cudaStream_t st);
 
 size_t fused_view_bytes(int kind);
 int fused_view_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes,

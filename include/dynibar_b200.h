@@ -202,6 +202,18 @@ int dyn_flow_sceneflow(const float* weights, const float* pts_seq,
                        int frame_idx, int sf_k, int n_flow, int R, int S,
                        float* flows, float* exp_sf, void* stream);
 
+/* ---- unit-test hook: the fused per-point stage (geometry_fc -> ray transformer
+ * -> heads; mlp_network.py:283-315 / :496-506) on caller-provided pooled
+ * features G [R*S, 272] (257 used) and nvalid [R*S].  Outputs the intermediates
+ * g2, Q, K, V, O [R*S,128]; dynamic net: out_a = raw [R*S,4]; static net:
+ * out_a = per-point part of rgb_fc.0 [R*S,128], out_b = masked sigma [R*S].
+ * posenc_ws: S*128 floats of scratch. */
+int dyn_debug_point_chain(dyn_net_t net, const float* G, const float* nvalid,
+                          const float* pts, const float* ray_dir, int R, int S,
+                          float* g2, float* Q, float* K, float* V, float* O,
+                          float* out_a, float* out_b, float* posenc_ws,
+                          void* stream);
+
 /* ---- building block: one nn.Linear on the tensor cores -----------------------
  * Y[M,N] = act(X[M,K] W[N,K]^T + b) with bf16 operands / fp32 accumulation
  * (tcgen05).  act: 0 none, 1 ELU, 2 ReLU, 3 sigmoid.  N <= 256.  packed_ws must
