@@ -4,13 +4,13 @@
   python bench.py --gpus N --steps K --warmup W              # this repo (CUDA)
   python bench.py --impl reference --gpus N --steps K ...    # CPU reference arm
 
-One "step" = every rank renders `--rays` rays (default: one 8192-ray eval
-chunk until the tensor-core path lands; a 512x288 frame is 147456 rays) of the
-synthetic 512x288 scene with 64 coarse + 64 fine samples and 8 dynamic + 8
-static source views through `render_rays_mv`, then the rendered pixels are
-gathered on rank 0 with one NCCL gather.  Per-GPU work is fixed as N grows
-("weak" scaling: N GPUs render N ray bundles -- e.g. N of the 11 held-out
-target views of an eval time step).  Prints ONE JSON line on rank 0.
+One "step" = every rank renders `--rays` rays (default 147456 = one full
+512x288 frame, in the reference's 8192-ray chunks) of the synthetic scene with
+64 coarse + 64 fine samples and 8 dynamic + 8 static source views through
+`render_rays_mv`, then the rendered pixels (rgb, depth, mask) are gathered on
+rank 0 with one NCCL gather.  Per-GPU work is fixed as N grows ("weak" scaling:
+N GPUs render N frames' worth of rays -- e.g. N of the 11 held-out target views
+of an eval time step).  Prints ONE JSON line on rank 0.
 """
 
 import argparse
@@ -36,7 +36,7 @@ def parse():
   ap.add_argument("--steps", type=int, default=3)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step")
+  ap.add_argument("--rays", type=int, default=147456, help="rays per GPU per step (147456 = one 512x288 frame)")
   ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
   ap.add_argument("--ref-rays", type=int, default=64, help="rays per step of the CPU reference arm")
   ap.add_argument("--cpu-rays", type=int, default=64, help="rays of the cpu_baseline sample")
@@ -148,7 +148,8 @@ def main():
                         "samples (fine pass evaluates 128), 8 dynamic + 8 static source views, "
                         "render_rays_mv, det=True, inv_uniform=True, chunk 8192",
             "rays_per_gpu_per_step": a.rays, "precision": a.precision,
-            "l2": "per-step intermediates (GBs) exceed the 126 MB L2; plus an explicit 256 MB flush between steps"}
+            "l2": "per-step working set (source maps 66 MB + GBs of per-chunk intermediates) exceeds the "
+                  "126 MB L2; plus an explicit 256 MB flush between steps"}
 
   if a.impl == "reference":
     if rank != 0:
@@ -166,7 +167,7 @@ def main():
     return 0
 
   import torch.distributed as dist
-  from dynibar_b200 import _lib, flops, render_ray as rr, synthetic
+  from dynibar_b200 import _lib, distributed as dd, flops, render_ray as rr, synthetic
   from dynibar_b200.projection import Projector
   dev = torch.device("cuda", local)
   torch.cuda.set_device(dev)
@@ -175,11 +176,13 @@ def main():
   rr.set_precision(a.precision)
 
   # every rank renders its own bundle of rays of the same scene (ray shard = rank)
-  batch, feat_c, feat_f, frame, t, offs, model, args = build_scene(a.rays * world)
-  sl = slice(rank * a.rays, (rank + 1) * a.rays)
+  # every rank renders `rays` rays of its own target view of the same scene
+  full = WORKLOAD["H"] * WORKLOAD["W"]
+  batch, feat_c, feat_f, frame, t, offs, model, args = build_scene(None if a.rays >= full else a.rays)
   host = dict(batch)
   for k in ("ray_o", "ray_d", "uv_grid"):
-    host[k] = batch[k][sl].contiguous()
+    reps = (a.rays + batch[k].shape[0] - 1) // batch[k].shape[0]
+    host[k] = batch[k].repeat(reps, 1)[:a.rays].contiguous()
   pin = lambda x: x.pin_memory() if torch.is_tensor(x) else x
   host = {k: pin(v) for k, v in host.items()}
   host_fc = tuple(pin(x) if x is not None else None for x in feat_c)
@@ -190,7 +193,6 @@ def main():
   fc_dev, ff_dev = synthetic.to_device(host_fc, dev), synthetic.to_device(host_ff, dev)
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
   out_host = torch.empty(a.rays, 5, pin_memory=True)
-  gather_buf = torch.empty(world, a.rays, 5, device=dev) if (world > 1 and rank == 0) else None
 
   def render(b, fc, ff):
     outs = []
@@ -204,7 +206,7 @@ def main():
       outs.append(torch.cat([r["rgb"], r["depth"][:, None], r["mask"][:, None].float()], 1))
     px = torch.cat(outs, 0)
     if world > 1:  # the path's one exchange step: rendered pixels -> rank 0 over NVLink
-      dist.gather(px, list(gather_buf.unbind(0)) if rank == 0 else None, dst=0)
+      dd.gather_pixels(px, a.rays * world)
     return px
 
   def step_resident():

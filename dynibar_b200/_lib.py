@@ -115,6 +115,17 @@ class Args(object):
   def __init__(self):
     self.keep = []
 
+  def host(self, t):
+    """Small per-frame arrays (cameras, basis): a HOST fp32 pointer is accepted by
+    the library and avoids a device read-back + stream sync inside the call."""
+    if t is None:
+      return None
+    c = t.detach().to(torch.float32).contiguous()
+    if c.is_cuda:
+      c = c.cpu()
+    self.keep.append(c)
+    return c.data_ptr()
+
   def __call__(self, t, dtype=torch.float32):
     if t is None:
       return None

@@ -368,10 +368,25 @@ static bool invert4(const double* m, double* inv) {
 // Cameras are tiny (34 floats per view); they are read back to the host once
 // per call to build the kernel-parameter structs.  `cams_dev` may also be a
 // host pointer (cudaMemcpyDefault).
-static int fetch_cams(const float* cams_dev, int V, float* host, cudaStream_t st) {
-  DYN_CUDA(cudaMemcpyAsync(host, cams_dev, sizeof(float) * 34 * V, cudaMemcpyDefault, st));
+// Small read-back helper: `src` may be a device OR a host pointer.  Host
+// pointers (what dynibar_b200/render_ray.py passes for cameras / basis rows) are
+// copied directly -- no stream synchronisation, so the kernel pipeline is not
+// drained once per call.
+int fetch_small(const float* src, size_t n_floats, float* host, cudaStream_t st) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, src);
+  if (e != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
+  if (at.type == cudaMemoryTypeUnregistered || at.type == cudaMemoryTypeHost) {
+    memcpy(host, src, sizeof(float) * n_floats);
+    return DYN_OK;
+  }
+  DYN_CUDA(cudaMemcpyAsync(host, src, sizeof(float) * n_floats, cudaMemcpyDefault, st));
   DYN_CUDA(cudaStreamSynchronize(st));
   return DYN_OK;
+}
+
+static int fetch_cams(const float* cams, int V, float* host, cudaStream_t st) {
+  return fetch_small(cams, (size_t)34 * V, host, st);
 }
 
 int build_view_cams(const float* src_cams, int V, const float* query_cam, cudaStream_t st,
@@ -477,12 +492,13 @@ int dyn_traj_displace(const float* pts, const float* coeff, const float* basis, 
   for (int v = 0; v < n_off; ++v) {
     int f = frame_idx + offsets_host[v];
     DYN_CHECK_ARG(f >= 0 && f < T);
-    DYN_CUDA(cudaMemcpyAsync(hb + 8 * v, basis + (size_t)f * nb, sizeof(float) * nb,
-                             cudaMemcpyDefault, st));
+    int rc = fetch_small(basis + (size_t)f * nb, nb, hb + 8 * v, st);
+    if (rc) return rc;
   }
-  DYN_CUDA(cudaMemcpyAsync(hb + 8 * n_off, basis + (size_t)frame_idx * nb, sizeof(float) * nb,
-                           cudaMemcpyDefault, st));
-  DYN_CUDA(cudaStreamSynchronize(st));
+  {
+    int rc = fetch_small(basis + (size_t)frame_idx * nb, nb, hb + 8 * n_off, st);
+    if (rc) return rc;
+  }
   for (int v = 0; v < n_off; ++v)
     for (int k = 0; k < nb; ++k) a.b_off[v][k] = hb[8 * v + k];
   for (int k = 0; k < nb; ++k) a.b_ref[k] = hb[8 * n_off + k];
@@ -569,10 +585,10 @@ int dyn_flow_sceneflow(const float* weights, const float* pts_seq, const float* 
   if (exp_sf != nullptr) {
     DYN_CHECK_ARG(coeff && basis && frame_idx - sf_k >= 0 && frame_idx + sf_k < T);
     float hb[24];
-    DYN_CUDA(cudaMemcpyAsync(hb, basis + (size_t)(frame_idx + sf_k) * nb, sizeof(float) * nb, cudaMemcpyDefault, st));
-    DYN_CUDA(cudaMemcpyAsync(hb + 8, basis + (size_t)(frame_idx - sf_k) * nb, sizeof(float) * nb, cudaMemcpyDefault, st));
-    DYN_CUDA(cudaMemcpyAsync(hb + 16, basis + (size_t)frame_idx * nb, sizeof(float) * nb, cudaMemcpyDefault, st));
-    DYN_CUDA(cudaStreamSynchronize(st));
+    int rc = fetch_small(basis + (size_t)(frame_idx + sf_k) * nb, nb, hb, st);
+    if (!rc) rc = fetch_small(basis + (size_t)(frame_idx - sf_k) * nb, nb, hb + 8, st);
+    if (!rc) rc = fetch_small(basis + (size_t)frame_idx * nb, nb, hb + 16, st);
+    if (rc) return rc;
     for (int k = 0; k < nb; ++k) { fc.b_p[k] = hb[k]; fc.b_m[k] = hb[8 + k]; fc.b_0[k] = hb[16 + k]; }
   }
   flow_sf_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(weights, pts_seq, uv, coeff, fc,

@@ -34,7 +34,7 @@ class Projector(object):
     front = torch.empty(V, N, dtype=torch.uint8, device=x.device)
     A = Args()
     with torch.cuda.device(x.device):
-      check(lib.dyn_compute_projections(ptr(x), A(train_cameras), V, N, ptr(pix),
+      check(lib.dyn_compute_projections(ptr(x), A.host(train_cameras), V, N, ptr(pix),
                                         ptr(front, torch.uint8), stream()))
     return pix.reshape(shape + (2,)), front.bool().reshape(shape)
 
@@ -72,7 +72,7 @@ def project_gather(xyz_st, xyz, query_camera, train_imgs, train_cameras, featmap
   with torch.cuda.device(dev):
     check(lib.dyn_project_gather(
         A(xyz_st), A(xyz),
-        A(query_camera), A(train_imgs), A(train_cameras), ptr(fm),
+        A.host(query_camera), A(train_imgs), A.host(train_cameras), ptr(fm),
         V, R, S, H, W, Cc, h, w, ws.data_ptr(), ptr(rgb_feat), ptr(ray_diff), ptr(mask),
         stream()))
   return rgb_feat, ray_diff, mask

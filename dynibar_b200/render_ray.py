@@ -139,7 +139,7 @@ def displaced_points(pts, coeff, basis, frame_idx, offsets, num_vv=0):
   offs = (C.c_int * max(n_off, 1))(*[int(o) for o in offsets])
   A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_traj_displace(A(pts), A(coeff), A(basis.to(dev)), T, nb,
+    check(lib.dyn_traj_displace(A(pts), A(coeff), A.host(basis), T, nb,
                                 int(frame_idx), offs, n_off, int(num_vv), R, S, ptr(seq), stream()))
   return seq
 
@@ -163,7 +163,7 @@ def compute_src_plucker_coordinate(pts, src_cameras):
   out = torch.empty(R, S, V, 6, device=dev_of(pts))
   A = Args()
   with torch.cuda.device(pts.device):
-    check(lib.dyn_plucker_src(A(pts), A(src_cameras), V, R, S, ptr(out), stream()))
+    check(lib.dyn_plucker_src(A(pts), A.host(src_cameras), V, R, S, ptr(out), stream()))
   return out
 
 
@@ -235,8 +235,8 @@ def net_static_fused(module, pts, ray_o, ray_d, query_cam, src_rgbs, src_cams, f
   ws = _lib.workspace.get(nbytes, dev)
   A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_net_static_fused(net.handle, A(pts), A(ray_o), A(ray_d), A(query_cam), A(src_rgbs),
-                                   A(src_cams), A(feat_cl), R, S, V, H, W, Cc, h, w, ptr(raw),
+    check(lib.dyn_net_static_fused(net.handle, A(pts), A(ray_o), A(ray_d), A.host(query_cam), A(src_rgbs),
+                                   A.host(src_cams), A(feat_cl), R, S, V, H, W, Cc, h, w, ptr(raw),
                                    ptr(mask), ws.data_ptr(), nbytes, stream()))
   return raw, mask
 
@@ -256,8 +256,8 @@ def net_dynamic_fused(module, pts, pts_seq, ray_dir, query_cam, src_rgbs, src_ca
   ws = _lib.workspace.get(nbytes, dev)
   A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_net_dynamic_fused(net.handle, A(pts), A(pts_seq), A(ray_dir), A(query_cam),
-                                    A(src_rgbs), A(src_cams), A(feat_cl), float(time), R, S, V, H, W,
+    check(lib.dyn_net_dynamic_fused(net.handle, A(pts), A(pts_seq), A(ray_dir), A.host(query_cam),
+                                    A(src_rgbs), A.host(src_cams), A(feat_cl), float(time), R, S, V, H, W,
                                     Cc, h, w, ptr(raw), ptr(mask), ws.data_ptr(), nbytes, stream()))
   return raw, mask
 
@@ -341,9 +341,9 @@ def _flow_sceneflow(weights, pts_seq, src_cameras, uv, coeff, basis, frame_idx, 
   A = Args()
   with torch.cuda.device(dev):
     check(lib.dyn_flow_sceneflow(
-        A(weights), A(pts_seq), A(src_cameras), A(uv),
+        A(weights), A(pts_seq), A.host(src_cameras), A(uv),
         A(coeff),
-        A(basis.to(dev) if basis is not None else None), T, nb, int(frame_idx), int(sf_k),
+        A.host(basis), T, nb, int(frame_idx), int(sf_k),
         int(n_flow), R, S, ptr(flows), ptr(exp_sf) if exp_sf is not None else None, stream()))
   return flows, exp_sf
 
@@ -359,6 +359,24 @@ def compute_optical_flow(outputs_coarse, raw_pts_3d_seq, src_cameras, uv_grid):
 # ---------------------------------------------------------------------------
 # a15 orchestrators
 # ---------------------------------------------------------------------------
+
+_HOST_KEYS = ("camera", "src_cameras", "static_src_cameras", "anchor_src_cameras", "depth_range")
+
+
+def _with_host_copies(ray_batch, model, basis_names):
+  """One device->host read of the tiny per-frame arrays (cameras, depth range,
+  trajectory basis) per render call instead of one per kernel launch."""
+  rb = dict(ray_batch)
+  for k in _HOST_KEYS:
+    v = ray_batch.get(k)
+    if torch.is_tensor(v) and v.is_cuda:
+      rb[k] = v.detach().float().cpu()
+  basis = {}
+  for name in basis_names:
+    b = getattr(model, name, None)
+    basis[name] = b.detach().float().cpu() if torch.is_tensor(b) else b
+  return rb, basis
+
 
 def _render_pass(ray_batch, feat_dy, feat_st, pts, z, s, t, frame_idx, offsets, num_vv, net_dy,
                  net_st, motion, basis, flow_views, sf_k, want_extras=True, want_vanilla_st=False):
@@ -418,18 +436,19 @@ def render_rays_mv(frame_idx, time_embedding, time_offset, ray_batch, model, pro
     offs = [int(o) for o in time_offset[0]]
     fidx = int(frame_idx[0])
     ret = {"outputs_coarse": None, "outputs_fine": None}
+    ray_batch, hb = _with_host_copies(ray_batch, model, ("trajectory_basis", "trajectory_basis_fine"))
     pts, z, _ = sample_along_camera_ray(ray_batch["ray_o"], ray_batch["ray_d"],
                                         ray_batch["depth_range"], N_samples, inv_uniform, det, jitter)
     out_c, _, _ = _render_pass(ray_batch, coarse_featmaps[0], coarse_featmaps[2], pts, z, None, t,
                                fidx, offs, 0, model.net_coarse_dy, model.net_coarse_st,
-                               model.motion_mlp, model.trajectory_basis, None, 2, want_extras=False)
+                               model.motion_mlp, hb["trajectory_basis"], None, 2, want_extras=False)
     ret["outputs_coarse_ref"] = out_c
     zf = resample_depths(z, out_c["weights"], N_importance, inv_uniform, det, u)
     pts_f, s = points_from_depths(ray_batch["ray_o"], ray_batch["ray_d"], zf,
                                   ray_batch["depth_range"])
     out_f, out_f_dy, _ = _render_pass(ray_batch, fine_featmaps[0], fine_featmaps[2], pts_f, zf, s,
                                       t, fidx, offs, 0, model.net_fine_dy, model.net_fine_st,
-                                      model.motion_mlp_fine, model.trajectory_basis_fine, None, 2)
+                                      model.motion_mlp_fine, hb["trajectory_basis_fine"], None, 2)
     ret["outputs_fine_ref"] = out_f
     ret["outputs_fine_ref_dy"] = out_f_dy
     ret["outputs_fine_anchor"] = None
@@ -448,11 +467,12 @@ def render_rays_mono(frame_idx, time_embedding, time_offset, ray_batch, model, f
                               "(render_ray.py:1099-1270) is scheduled after the forward path")
   with torch.no_grad():
     t = _scalar(time_embedding[0].float())
+    ray_batch, hb = _with_host_copies(ray_batch, model, ("trajectory_basis",))
     pts, z, s = sample_along_camera_ray(ray_batch["ray_o"], ray_batch["ray_d"],
                                         ray_batch["depth_range"], N_samples, inv_uniform, det, jitter)
     out, out_dy, out_st = _render_pass(ray_batch, featmaps[0], featmaps[2], pts, z, s, t,
                                        int(frame_idx[0]), [int(o) for o in time_offset[0]], num_vv,
                                        model.net_coarse_dy, model.net_coarse_st, model.motion_mlp,
-                                       model.trajectory_basis, 6, 1, want_vanilla_st=True)
+                                       hb["trajectory_basis"], 6, 1, want_vanilla_st=True)
   return {"outputs_coarse": None, "outputs_fine": None, "outputs_coarse_ref": out,
           "outputs_coarse_ref_dy": out_dy, "outputs_coarse_st": out_st}

@@ -10,6 +10,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
  *     tensors are dense row-major fp32 unless stated; shapes in comments.
+ *     The tiny per-frame arrays (`*_cam`, `*_cams`, `basis`) may be HOST
+ *     pointers as well: host copies are read without synchronising the stream.
  *   - the caller owns every buffer (inputs, outputs, workspace, packed
  *     weights); the library never allocates or frees device memory and keeps
  *     no device pointer after return except inside a `dyn_net_t` handle.

@@ -240,3 +240,27 @@ def test_full_size_properties(rr):
   z = full["z_vals"]
   assert (z[:, 1:] >= z[:, :-1]).all() and z.shape == (1024, 128)
   assert torch.isfinite(full["rgb"]).all() and full["mask"].dtype == torch.bool
+
+
+def test_render_single_image_driver(rr, golden):
+  """Frame driver (render_image.py:9-217): same structure as the reference's (CPU tensors
+  reshaped to [H,W,...], rgb zeroed where mask == 0) and identical to one un-chunked call."""
+  from dynibar_b200.projection import Projector
+  from dynibar_b200.render_image import render_single_image_nvi
+  cfg = dict(scenes.GOLDEN_CONFIGS["mv_small"], rays=None, H=12, W=16)
+  batch, feat_c, feat_f, frame, t, offs, model, args = scenes.build(cfg)
+  b, fc, ff = _dev(batch), _dev(feat_c), _dev(feat_f)
+  m = synthetic.model_to(model, DEV)
+  sampler = type("S", (), {"H": 12, "W": 16})()
+  ret = render_single_image_nvi(frame, t, offs, sampler, b, m, Projector(DEV), 50, cfg["N_samples"], args,
+                                inv_uniform=True, N_importance=cfg["N_importance"], det=True,
+                                coarse_featmaps=fc, fine_featmaps=ff, is_train=False)
+  assert list(ret.keys()) == ["outputs_fine_anchor", "outputs_fine_ref", "outputs_coarse_ref", "outputs_fine"]
+  one = rr.render_rays_mv(frame, t, offs, b, m, Projector(DEV), fc, ff, cfg["N_samples"], args,
+                          inv_uniform=True, N_importance=cfg["N_importance"], det=True, is_train=False)
+  f = ret["outputs_fine_ref"]
+  assert not f["rgb"].is_cuda and f["rgb"].shape == (12, 16, 3) and f["depth"].shape == (12, 16)
+  assert f["weights"].shape == (12, 16, 32) and f["render_flows"].shape == (7, 12, 16, 2)
+  want = one["outputs_fine_ref"]["rgb"].cpu().masked_fill(~one["outputs_fine_ref"]["mask"].cpu()[:, None], 0.0)
+  assert torch.equal(f["rgb"].reshape(-1, 3), want)
+  assert torch.equal(f["depth"].reshape(-1), one["outputs_fine_ref"]["depth"].cpu())
