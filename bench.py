@@ -14,6 +14,7 @@ of an eval time step).  Prints ONE JSON line on rank 0.
 """
 
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -25,6 +26,16 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
+
+KERNEL_CLASSES = ["view_static", "view_dynamic", "motion", "point1", "point2", "rgbhead", "attention",
+                  "gather"]
+# algorithmic MACs per row of each fused kernel (dynibar_b200/flops.py, reference layer widths)
+#   view_*: per (point, view); motion/point*: per point; rgbhead: per (point, view)
+KERNEL_MAC = {"view_static": 35328 + 2310 + 86528 + 32896 + 16512, "view_dynamic": 123392,
+              "motion": 530944, "point1": 98560 + 3 * 16384, "rgbhead": 41664}
+# DRAM bytes per (point, view) row of the static per-view kernel from the committed ncu capture
+# profiles/r01_view_static_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum per launch / rows)
+NCU_DRAM_BYTES_PER_ROW = {"view_static": 626.3}
 
 WORKLOAD = dict(H=288, W=512, V_dy=8, V_st=8, N_samples=64, N_importance=64, chunk=8192, seed=0)
 METRIC = "rays/sec (64+64 samples x 8 src views)"
@@ -244,9 +255,17 @@ def main():
   sampler = ClockSampler(local)
   sampler.start()
   _lib.lib.dyn_launch_count(1)
+  _lib.lib.dyn_profile_enable(1)  # CUDA events around the big kernels, on their launching stream
   ms = timed(step_resident, a.steps)
   launches = int(_lib.lib.dyn_launch_count(0))
   clocks = sampler.finish()
+  kernel_ms = {}
+  for cls, name in enumerate(KERNEL_CLASSES):
+    tot, n = ctypes.c_float(), ctypes.c_int()
+    _lib.check(_lib.lib.dyn_profile_read(cls, ctypes.byref(tot), ctypes.byref(n)))
+    if n.value:
+      kernel_ms[name] = (tot.value, n.value)
+  _lib.lib.dyn_profile_enable(0)
   step_e2e()
   ms_e2e = timed(step_e2e, a.steps)
 
@@ -261,6 +280,18 @@ def main():
     pk = peaks()
     fpr = flops.flop_per_ray(w["N_samples"], w["N_samples"] + w["N_importance"], w["V_dy"], w["V_st"])
     achieved = (a.rays * a.steps / (ms / 1e3)) * fpr / 1e12  # per GPU
+    # dominant kernel (largest share of device time on rank 0), timed live with CUDA events
+    S_tot = w["N_samples"] + (w["N_samples"] + w["N_importance"])
+    rows_step = {"view_static": a.rays * S_tot * w["V_st"], "view_dynamic": a.rays * S_tot * w["V_dy"],
+                 "motion": a.rays * S_tot, "point1": 2 * a.rays * S_tot, "rgbhead": a.rays * S_tot * w["V_st"]}
+    kernels = {}
+    for name, (tot_ms, n) in kernel_ms.items():
+      k = {"ms_per_step": tot_ms / a.steps, "launches_per_step": n / a.steps,
+           "share_of_step": tot_ms / ms}
+      if name in KERNEL_MAC:
+        k["tflops"] = rows_step[name] * a.steps * KERNEL_MAC[name] * 2 / (tot_ms / 1e3) / 1e12
+      kernels[name] = k
+    dom = max((n for n in kernels if n in KERNEL_MAC), key=lambda n: kernels[n]["ms_per_step"], default=None)
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
@@ -268,11 +299,24 @@ def main():
         "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"],
-                     "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": None,
-                     "flop_per_ray": fpr, "peak_source": pk["source"] + ", sustained bf16",
-                     "scope": "whole step (all kernels of render_rays_mv), per GPU"},
+        "roofline_step": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"],
+                          "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+                          "flop_per_ray": fpr, "peak_source": pk["source"] + ", sustained bf16",
+                          "scope": "whole step (all kernels of render_rays_mv), per GPU"},
+        "kernels": kernels,
     }
+    if dom is not None:
+      kd = kernels[dom]
+      rows_launch = rows_step[dom] / kd["launches_per_step"]
+      line["roofline"] = {
+          "kernel": dom, "bound": "tensor", "achieved": kd["tflops"], "peak": pk["tf_sustained"],
+          "unit": "TFLOP/s", "frac": kd["tflops"] / pk["tf_sustained"],
+          "traffic": (NCU_DRAM_BYTES_PER_ROW[dom] * rows_launch if dom in NCU_DRAM_BYTES_PER_ROW else None),
+          "algorithmic_flop_per_launch": rows_launch * KERNEL_MAC[dom] * 2,
+          "avg_launch_ms": kd["ms_per_step"] / kd["launches_per_step"],
+          "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+          "how": "CUDA events recorded by the library on the launching stream around every launch of "
+                 "this kernel inside the timed region (dyn_profile_*)"}
     if world == 1 and not a.no_cpu_baseline:
       cv, csec = run_oracle(a.cpu_rays, 1, 1)
       line["cpu_baseline"] = {"value": cv, "unit": "rays/s", "cores": cpu_threads(), "kind": "port",

@@ -31,6 +31,8 @@ SIGNATURES = {
     "dyn_last_error": (C.c_char_p, []),
     "dyn_device_sm_count": (_i, []),
     "dyn_launch_count": (C.c_ulonglong, [_i]),
+    "dyn_profile_enable": (None, [_i]),
+    "dyn_profile_read": (_i, [_i, C.POINTER(C.c_float), C.POINTER(_i)]),
     "dyn_net_param_count": (_sz, [_i]),
     "dyn_net_packed_bytes": (_sz, [_i]),
     "dyn_net_create": (_i, [_i, _vp, _sz, _vp, _i, _f, _i, _i, _vp, C.POINTER(_vp)]),

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "linear_tc.cuh"
 #include "nets.cuh"
 #include "nets_fused.cuh"
@@ -9,6 +11,28 @@
 namespace dyn {
 
 unsigned long long g_launches = 0;
+
+// ---- profiling hook ----
+static int g_prof_on = 0;
+struct ProfPair { cudaEvent_t a, b; int cls; };
+static std::vector<ProfPair> g_prof;
+static cudaEvent_t g_prof_open[PROF_NCLASS];
+
+void prof_begin(int cls, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_prof_open[cls] = e;
+}
+void prof_end(int cls, cudaStream_t st) {
+  if (!g_prof_on || !g_prof_open[cls]) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_prof.push_back(ProfPair{g_prof_open[cls], e, cls});
+  g_prof_open[cls] = nullptr;
+}
 
 char* err_buf() {
   static thread_local char buf[512] = {0};
@@ -44,6 +68,31 @@ int dyn_device_sm_count(void) {
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
   return n;
+}
+
+void dyn_profile_enable(int on) {
+  g_prof_on = on;
+  if (on) {
+    for (auto& p : g_prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    g_prof.clear();
+  }
+}
+
+int dyn_profile_read(int cls, float* total_ms, int* launches) {
+  DYN_CHECK_ARG(cls >= 0 && cls < PROF_NCLASS && total_ms && launches);
+  float tot = 0.f;
+  int n = 0;
+  for (auto& p : g_prof) {
+    if (p.cls != cls) continue;
+    DYN_CUDA(cudaEventSynchronize(p.b));
+    float ms = 0.f;
+    DYN_CUDA(cudaEventElapsedTime(&ms, p.a, p.b));
+    tot += ms;
+    ++n;
+  }
+  *total_ms = tot;
+  *launches = n;
+  return DYN_OK;
 }
 
 size_t dyn_net_param_count(int kind) {

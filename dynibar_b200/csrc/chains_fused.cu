@@ -698,6 +698,7 @@ int launch_motion_fused(const dyn_net* n, MotionFusedArgs& a, cudaStream_t st) {
   for (int i = 0; i < 8; ++i) a.o_bias[i] = n->ml.pts[i].b;
   a.o_bias[8] = n->ml.coeff.b;
   a.ncoef = 3 * n->nb;
+  ProfScope prof(PROF_MOTION, st);
   return launch_chain(motion_fused_kernel, a, a.N, st);
 }
 
@@ -708,6 +709,7 @@ int launch_point1_fused(const dyn_net* n, Point1Args& a, cudaStream_t st) {
   a.params = n->params;
   a.o_bgeo0 = dynamic ? n->dl.geo0.b : n->sl.geo0.b;
   a.o_bgeo2 = dynamic ? n->dl.geo2.b : n->sl.geo2.b;
+  ProfScope prof(PROF_POINT1, st);
   return launch_chain(point1_fused_kernel, a, a.P, st);
 }
 
@@ -717,6 +719,7 @@ int launch_point2_fused(const dyn_net* n, Point2Args& a, cudaStream_t st) {
   a.wimg = n->chain[1].img; a.chunks = n->chain[1].tab; a.nchunks = n->chain[1].nchunks;
   a.params = n->params;
   a.shift = n->shift;
+  ProfScope prof(PROF_POINT2, st);
   if (dynamic) {
     const DynamicLayout& L = n->dl;
     a.o_lnw = L.ln_w; a.o_lnb = L.ln_b; a.o_brefpts0 = L.refpts0.b; a.o_brefpts2 = L.refpts2.b;
@@ -736,6 +739,7 @@ int launch_rgbhead_fused(const dyn_net* n, RgbHeadArgs& a, cudaStream_t st) {
   a.wimg = n->chain[2].img; a.chunks = n->chain[2].tab; a.nchunks = n->chain[2].nchunks;
   a.params = n->params;
   a.o_brgb2 = n->sl.rgb2.b; a.o_wrgb4 = n->sl.rgb4.w; a.o_brgb4 = n->sl.rgb4.b;
+  ProfScope prof(PROF_RGBHEAD, st);
   if (a.V <= 8) return launch_chain(rgbhead_fused_kernel<8>, a, a.P * 8, st);
   return launch_chain(rgbhead_fused_kernel<16>, a, a.P * 16, st);
 }

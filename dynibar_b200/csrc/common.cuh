@@ -38,6 +38,18 @@ extern unsigned long long g_launches;
     DYN_CUDA(cudaGetLastError());     \
   } while (0)
 
+// ---- optional per-kernel-class device timing (dyn_profile_*): CUDA events on the
+// launching stream around the big fused kernels; off by default.
+enum ProfClass { PROF_VIEW_ST = 0, PROF_VIEW_DY, PROF_MOTION, PROF_POINT1, PROF_POINT2, PROF_RGBHEAD,
+                 PROF_ATTENTION, PROF_GATHER, PROF_NCLASS };
+void prof_begin(int cls, cudaStream_t st);
+void prof_end(int cls, cudaStream_t st);
+struct ProfScope {
+  int cls; cudaStream_t st;
+  ProfScope(int c, cudaStream_t s) : cls(c), st(s) { prof_begin(c, s); }
+  ~ProfScope() { prof_end(cls, st); }
+};
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kC = 32;      // feature channels (coarse_feat_dim / fine_feat_dim)

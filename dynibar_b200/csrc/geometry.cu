@@ -525,6 +525,7 @@ int dyn_project_gather(const float* xyz_st, const float* xyz, const float* query
   DYN_LAUNCH_CHECK();
   long long N = (long long)R * S;
   long long threads = N * V * 8;
+  ProfScope prof(PROF_GATHER, st);
   project_gather_kernel<<<cdiv(threads, 256), 256, 0, st>>>(xyz_st, xyz, src_rgbs, feat_cl_ws, vc,
                                                             V, N, H, W, h, w, rgb_feat, ray_diff,
                                                             mask);

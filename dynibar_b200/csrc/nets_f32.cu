@@ -871,6 +871,7 @@ static int run_point_fused(const dyn_net* n, const float* G, long long P, int R,
     if (smem > 48 * 1024)
       DYN_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
+    ProfScope prof(PROF_ATTENTION, st);
     attention_kernel<<<R, threads, smem, st>>>(t.Q, t.K, t.V, t.nvalid, S, t.O);
     DYN_LAUNCH_CHECK();
   }

@@ -563,6 +563,7 @@ int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
   const long long n_iter = (a.P * VP + 255) / 256;
   const int grid = (int)(n_iter < sms ? n_iter : sms);
   if (grid == 0) return DYN_OK;
+  ProfScope prof(st_net ? PROF_VIEW_ST : PROF_VIEW_DY, st);
 #define LAUNCH_VF(VPV, STV)                                                                   \
   do {                                                                                        \
     DYN_CUDA(cudaFuncSetAttribute(view_fused_kernel<VPV, STV>,                                \

@@ -53,6 +53,14 @@ int dyn_device_sm_count(void);
 /* Kernels launched by this library since load (or the last reset). */
 unsigned long long dyn_launch_count(int reset);
 
+/* Optional device timing of the big kernels (CUDA events on the launching
+ * stream, recorded inside the library around each launch).  Classes: 0 fused
+ * static per-view stage, 1 fused dynamic per-view stage, 2 MotionMLP, 3 point
+ * stage 1, 4 point stage 2, 5 static blending head, 6 ray-transformer attention,
+ * 7 stand-alone projection+gather.  enable(1) clears previous records. */
+void dyn_profile_enable(int on);
+int dyn_profile_read(int cls, float* total_ms, int* launches);
+
 /* ---- weights ------------------------------------------------------------
  * `params` is the flat fp32 concatenation of the network's state_dict tensors
  * in the canonical order documented in dynibar_b200/weights.py (reference key
