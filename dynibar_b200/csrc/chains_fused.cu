@@ -23,15 +23,10 @@ using namespace fe;
 namespace {
 
 // common prologue: barriers + TMEM; returns the TMEM base address
-__device__ __forceinline__ uint32_t fused_prologue(uint64_t* bars, uint32_t* tmem_slot) {
+__device__ __forceinline__ uint32_t fused_prologue(uint64_t* bars, uint32_t* tmem_slot, bool pp) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
-  if (tid == 0) {
-    for (int i = 0; i < kRing; ++i) { mbar_init(bar0 + 8u * i, 1); mbar_init(bar0 + 8u * (4 + i), 1); }
-    mbar_init(bar0 + 8u * 8, 256);
-    mbar_init(bar0 + 8u * 9, 1);
-    mbar_fence_init();
-  }
+  if (tid == 0) init_barriers(bar0, pp);
   if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before_sync();
   __syncthreads();
@@ -45,13 +40,14 @@ __device__ __forceinline__ void fused_teardown(uint32_t tmem_base) {
     tmem_dealloc(tmem_base, 512);
   }
 }
-__device__ __forceinline__ void operand_ready(uint32_t bar0) {
+// `bt` = barrier tile: the thread's tile in ping-pong kernels, 0 in lock-step kernels
+__device__ __forceinline__ void operand_ready(uint32_t bar0, int bt) {
   fence_proxy_async_smem();
   tc_fence_before_sync();
-  mbar_arrive(bar0 + 8u * 8);
+  mbar_arrive(bar_aready(bar0, bt));
 }
-__device__ __forceinline__ void wait_acc(uint32_t bar0, uint32_t& acc_cnt) {
-  mbar_wait(bar0 + 8u * 9, acc_cnt & 1);
+__device__ __forceinline__ void wait_acc(uint32_t bar0, int bt, uint32_t& acc_cnt) {
+  mbar_wait(bar_acc(bar0, bt), acc_cnt & 1);
   ++acc_cnt;
   tc_fence_after_sync();
 }
@@ -109,24 +105,26 @@ __device__ __forceinline__ void motion_operand(uint8_t* arow, const float* x4, b
 }
 
 __global__ void __launch_bounds__(320, 1) motion_fused_kernel(const __grid_constant__ MotionFusedArgs a) {
+  constexpr bool kPP = false;  // MMA-bound ReLU chain: share every weight chunk between the tiles
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem + 2 * kATileBytes;
   float* cst = reinterpret_cast<float*>(ring + kRing * kStageBytes);  // 8 x 256 biases + 32
   uint64_t* bars = reinterpret_cast<uint64_t*>(cst + 2304);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
   for (int i = tid; i < 2048; i += blockDim.x) cst[i] = a.params[a.o_bias[i >> 8] + (i & 255)];
   if (tid < 32) cst[2048 + tid] = tid < a.ncoef ? a.params[a.o_bias[8] + tid] : 0.f;
-  const uint32_t tmem_base = fused_prologue(bars, tmem_slot);
+  const uint32_t tmem_base = fused_prologue(bars, tmem_slot, kPP);
   const int n_iter = (int)((a.N + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<kPP>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 8) {
-    if ((tid & 31) == 0) issuer_loop(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
+    if ((tid & 31) == 0) issuer_loop<kPP>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
     const int tile = tid >> 7, r = tid & 127;
+    const int bt = kPP ? tile : 0;
     uint8_t* arow = smem + tile * kATileBytes + (r >> 3) * 128 + (r & 7) * 16;
     const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(tile * 256));
     uint32_t acc_cnt = 0;
@@ -140,24 +138,24 @@ __global__ void __launch_bounds__(320, 1) motion_fused_kernel(const __grid_const
         if (a.time_is_column) x4[3] = src[3];
       }
       motion_operand(arow, x4, valid);
-      operand_ready(bar0);
+      operand_ready(bar0, bt);
       for (int l = 0; l < 5; ++l) {  // pts_linears.0 .. 4
-        wait_acc(bar0, acc_cnt);
+        wait_acc(bar0, bt, acc_cnt);
         epi_cols_to_A<2>(arow, tacc, 256, cst + 256 * l);
-        operand_ready(bar0);
+        operand_ready(bar0, bt);
       }
       // pts_linears.5 on cat([input_pts, h]): h part consumed first, then the
       // operand tile is re-filled with PE(xyzt) and the MMA keeps accumulating
-      wait_acc(bar0, acc_cnt);
+      wait_acc(bar0, bt, acc_cnt);
       motion_operand(arow, x4, valid);
-      operand_ready(bar0);
+      operand_ready(bar0, bt);
       for (int l = 5; l < 8; ++l) {  // epilogues of pts_linears.5 .. 7
-        wait_acc(bar0, acc_cnt);
+        wait_acc(bar0, bt, acc_cnt);
         epi_cols_to_A<2>(arow, tacc, 256, cst + 256 * l);
-        operand_ready(bar0);
+        operand_ready(bar0, bt);
       }
       // coeff_linear (18 of 32 columns), zero the last samples of each ray
-      wait_acc(bar0, acc_cnt);
+      wait_acc(bar0, bt, acc_cnt);
       float acc[32];
       tmem_ld32(tacc, acc);
       tmem_wait_ld();
@@ -178,24 +176,26 @@ __global__ void __launch_bounds__(320, 1) motion_fused_kernel(const __grid_const
 // per-point stage 1: G -> geometry_fc -> (+ posenc) -> g2, Q, K, V
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_constant__ Point1Args a) {
+  constexpr bool kPP = true;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem + 2 * kATileBytes;
   float* cst = reinterpret_cast<float*>(ring + kRing * kStageBytes);  // b_geo0[256] b_geo2[128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(cst + 2304);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
   for (int i = tid; i < 256; i += blockDim.x) cst[i] = a.params[a.o_bgeo0 + i];
   for (int i = tid; i < 128; i += blockDim.x) cst[256 + i] = a.params[a.o_bgeo2 + i];
-  const uint32_t tmem_base = fused_prologue(bars, tmem_slot);
+  const uint32_t tmem_base = fused_prologue(bars, tmem_slot, kPP);
   const int n_iter = (int)((a.P + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<kPP>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 8) {
-    if ((tid & 31) == 0) issuer_loop(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
+    if ((tid & 31) == 0) issuer_loop<kPP>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
     const int tile = tid >> 7, r = tid & 127;
+    const int bt = kPP ? tile : 0;
     uint8_t* arow = smem + tile * kATileBytes + (r >> 3) * 128 + (r & 7) * 16;
     const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(tile * 256));
     uint32_t acc_cnt = 0;
@@ -218,11 +218,11 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
           store8(arow, 8 * g, v);
         }
       }
-      operand_ready(bar0);
-      wait_acc(bar0, acc_cnt);  // geometry_fc.0
+      operand_ready(bar0, bt);
+      wait_acc(bar0, bt, acc_cnt);  // geometry_fc.0
       epi_cols_to_A<1>(arow, tacc, 256, cst);
-      operand_ready(bar0);
-      wait_acc(bar0, acc_cnt);  // geometry_fc.2 (+ sinusoid for the dynamic net) -> g2
+      operand_ready(bar0, bt);
+      wait_acc(bar0, bt, acc_cnt);  // geometry_fc.2 (+ sinusoid for the dynamic net) -> g2
       {
         const int s_idx = valid ? (int)(row % a.S) : 0;
 #pragma unroll 1
@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
           for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
         }
       }
-      operand_ready(bar0);
-      wait_acc(bar0, acc_cnt);  // [Wq ; Wk] (N = 256, no bias)
+      operand_ready(bar0, bt);
+      wait_acc(bar0, bt, acc_cnt);  // [Wq ; Wk] (N = 256, no bias)
 #pragma unroll 1
       for (int cb = 0; cb < 256; cb += 32) {
         float acc[32];
@@ -260,8 +260,8 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(bar0 + 8u * 8);  // operand unchanged; accumulators are free again
-      wait_acc(bar0, acc_cnt);     // Wv
+      mbar_arrive(bar_aready(bar0, bt));  // operand unchanged; accumulators are free again
+      wait_acc(bar0, bt, acc_cnt);     // Wv
 #pragma unroll 1
       for (int cb = 0; cb < 128; cb += 32) {
         float acc[32];
@@ -287,11 +287,12 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
 // ---------------------------------------------------------------------------
 template <bool DYNAMIC>
 __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_constant__ Point2Args a) {
+  constexpr bool kPP = true;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem + 2 * kATileBytes;
   float* cst = reinterpret_cast<float*>(ring + kRing * kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(cst + 2304);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
   {
@@ -310,15 +311,16 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
     }
     if (tid == 0) cst[1280] = p[a.o_boutgeo2];
   }
-  const uint32_t tmem_base = fused_prologue(bars, tmem_slot);
+  const uint32_t tmem_base = fused_prologue(bars, tmem_slot, kPP);
   const int n_iter = (int)((a.P + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<kPP>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 8) {
-    if ((tid & 31) == 0) issuer_loop(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
+    if ((tid & 31) == 0) issuer_loop<kPP>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
     const int tile = tid >> 7, r = tid & 127;
+    const int bt = kPP ? tile : 0;
     uint8_t* arow = smem + tile * kATileBytes + (r >> 3) * 128 + (r & 7) * 16;
     const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(tile * 256));
     uint32_t acc_cnt = 0;
@@ -339,8 +341,8 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
           store8(arow, 8 * g, v);
         }
       }
-      operand_ready(bar0);
-      wait_acc(bar0, acc_cnt);  // fc (no bias) + residual, LayerNorm (eps 1e-6) via TMEM scratch
+      operand_ready(bar0, bt);
+      wait_acc(bar0, bt, acc_cnt);  // fc (no bias) + residual, LayerNorm (eps 1e-6) via TMEM scratch
       {
         float sum = 0.f, sq = 0.f;
 #pragma unroll 1
@@ -383,11 +385,11 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
         for (int i = 33; i < 48; ++i) pe[i] = 0.f;
 #pragma unroll
         for (int g = 0; g < 6; ++g) store8(arow, 128 + 8 * g, pe + 8 * g);
-        operand_ready(bar0);
-        wait_acc(bar0, acc_cnt);  // ref_pts_fc.0
+        operand_ready(bar0, bt);
+        wait_acc(bar0, bt, acc_cnt);  // ref_pts_fc.0
         epi_cols_to_A<1>(arow, tacc, 256, cst + 256);
-        operand_ready(bar0);
-        wait_acc(bar0, acc_cnt);  // ref_pts_fc.2 -> g4; append PE(dir) (27) at 128..154
+        operand_ready(bar0, bt);
+        wait_acc(bar0, bt, acc_cnt);  // ref_pts_fc.2 -> g4; append PE(dir) (27) at 128..154
         epi_cols_to_A<1>(arow, tacc, 128, cst + 512);
         {
           const long long ray = valid ? row / a.S : 0;
@@ -400,9 +402,9 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
           for (int g = 0; g < 4; ++g) store8(arow, 128 + 8 * g, pe2 + 8 * g);
         }
       }
-      operand_ready(bar0);
+      operand_ready(bar0, bt);
       // round: out_geometry_fc.0 -> cols [0,128), rgb_fc.0 (dyn) / rgb_fc.0[:, :128] (static) -> [128,256)
-      wait_acc(bar0, acc_cnt);
+      wait_acc(bar0, bt, acc_cnt);
       float sigma = cst[1280];
 #pragma unroll 1
       for (int cb = 0; cb < 128; cb += 32) {
@@ -416,8 +418,8 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
       const float nv = valid ? a.nvalid[row] : 0.f;
       if (DYNAMIC) {
         epi_cols_to_A<1>(arow, tacc + 128, 128, cst + 896);  // ELU(rgb_fc.0) -> operand
-        operand_ready(bar0);
-        wait_acc(bar0, acc_cnt);  // rgb_fc.2 (64) -> rgb_fc.4 (3) as dot products
+        operand_ready(bar0, bt);
+        wait_acc(bar0, bt, acc_cnt);  // rgb_fc.2 (64) -> rgb_fc.4 (3) as dot products
         float c3[3] = {cst[1281], cst[1282], cst[1283]};
 #pragma unroll 1
         for (int cb = 0; cb < 64; cb += 32) {
@@ -467,11 +469,12 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
 // ---------------------------------------------------------------------------
 template <int VP>
 __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_constant__ RgbHeadArgs a) {
+  constexpr bool kPP = true;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem + 2 * kATileBytes;
   float* cst = reinterpret_cast<float*>(ring + kRing * kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(cst + 2304);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
   for (int i = tid; i < 64; i += blockDim.x) {
@@ -479,15 +482,16 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
     cst[192 + i] = a.params[a.o_wrgb4 + i];
   }
   if (tid == 0) cst[256] = a.params[a.o_brgb4];
-  const uint32_t tmem_base = fused_prologue(bars, tmem_slot);
+  const uint32_t tmem_base = fused_prologue(bars, tmem_slot, kPP);
   const int n_iter = (int)((a.P * VP + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<kPP>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 8) {
-    if ((tid & 31) == 0) issuer_loop(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
+    if ((tid & 31) == 0) issuer_loop<kPP>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
     const int tile = tid >> 7, r = tid & 127;
+    const int bt = kPP ? tile : 0;
     uint8_t* arow = smem + tile * kATileBytes + (r >> 3) * 128 + (r & 7) * 16;
     const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(tile * 256));
     const int v = tid % VP;
@@ -519,8 +523,8 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
         float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         store8(arow, 136, z);
       }
-      operand_ready(bar0);
-      wait_acc(bar0, acc_cnt);  // rgb_fc.0: per-view part + per-point part GW (bias folded into GW)
+      operand_ready(bar0, bt);
+      wait_acc(bar0, bt, acc_cnt);  // rgb_fc.0: per-view part + per-point part GW (bias folded into GW)
 #pragma unroll 1
       for (int cb = 0; cb < 128; cb += 32) {
         float acc[32];
@@ -536,8 +540,8 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
 #pragma unroll
         for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
       }
-      operand_ready(bar0);
-      wait_acc(bar0, acc_cnt);  // rgb_fc.2 (64, ELU) -> rgb_fc.4 logit
+      operand_ready(bar0, bt);
+      wait_acc(bar0, bt, acc_cnt);  // rgb_fc.2 (64, ELU) -> rgb_fc.4 logit
       float logit = cst[256];
 #pragma unroll 1
       for (int cb = 0; cb < 64; cb += 32) {

@@ -105,56 +105,95 @@ __device__ __forceinline__ void rs_step(const float* in, float* out, bool upper,
 
 
 // ---- control warps (one elected lane each) -------------------------------------
-// weight producer: streams the chunk table once per iteration through the ring
+// barrier slots: [0..3] w_full, [4..7] w_empty, [8] a_ready(tile0), [9] acc_full(tile0),
+//                [10] a_ready(tile1), [11] acc_full(tile1)
+// Two schedules:
+//   lock-step (PP = false): both 128-row tiles consume every weight chunk together
+//     (weights stream once per 256 rows); one a_ready (256 arrivals) / acc_full pair.
+//   ping-pong (PP = true): per ROUND (chunks from a wait-flag to a last-flag) tile 0
+//     then tile 1, each with its own barriers (128 arrivals), so the MMA of one tile
+//     overlaps the epilogue of the other; weights stream twice.
+__device__ __forceinline__ uint32_t bar_aready(uint32_t bar0, int tile) { return bar0 + 8u * (8 + 2 * tile); }
+__device__ __forceinline__ uint32_t bar_acc(uint32_t bar0, int tile) { return bar0 + 8u * (9 + 2 * tile); }
+
+__device__ __forceinline__ void init_barriers(uint32_t bar0, bool pp) {
+  for (int i = 0; i < kRing; ++i) { mbar_init(bar0 + 8u * i, 1); mbar_init(bar0 + 8u * (4 + i), 1); }
+  mbar_init(bar_aready(bar0, 0), pp ? 128 : 256);
+  mbar_init(bar_acc(bar0, 0), 1);
+  mbar_init(bar_aready(bar0, 1), 128);
+  mbar_init(bar_acc(bar0, 1), 1);
+  mbar_fence_init();
+}
+
+__device__ __forceinline__ int round_end(const FusedChunk* __restrict__ chunks, int c0, int nchunks) {
+  int c = c0;
+  while (c < nchunks && !(chunks[c].flags & 2)) ++c;
+  return c + 1 < nchunks ? c + 1 : nchunks;
+}
+
+template <bool PP>
 __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chunks, int nchunks,
                                               const void* wimg, int n_iter, uint8_t* ring, uint32_t bar0) {
   const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(wimg);
   uint32_t cnt = 0;
   for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
-    for (int c = 0; c < nchunks; ++c, ++cnt) {
-      const uint32_t st = cnt % kRing;
-      if (cnt >= kRing) mbar_wait(bar0 + 8u * (4 + st), ((cnt / kRing) - 1) & 1);
-      const FusedChunk ch = chunks[c];
-      mbar_arrive_expect_tx(bar0 + 8u * st, ch.bytes);
-      bulk_g2s(smem_u32(ring + st * kStageBytes), wsrc + ch.off, ch.bytes, bar0 + 8u * st);
+    for (int c0 = 0; c0 < nchunks;) {
+      const int c1 = PP ? round_end(chunks, c0, nchunks) : nchunks;
+      for (int rep = 0; rep < (PP ? 2 : 1); ++rep) {
+        for (int c = c0; c < c1; ++c, ++cnt) {
+          const uint32_t st = cnt % kRing;
+          if (cnt >= kRing) mbar_wait(bar0 + 8u * (4 + st), ((cnt / kRing) - 1) & 1);
+          const FusedChunk ch = chunks[c];
+          mbar_arrive_expect_tx(bar0 + 8u * st, ch.bytes);
+          bulk_g2s(smem_u32(ring + st * kStageBytes), wsrc + ch.off, ch.bytes, bar0 + 8u * st);
+        }
+      }
+      c0 = c1;
     }
   }
 }
 
-// MMA issuer: per chunk, both 128-row tiles consume the same weight stage.
 // FusedChunk.flags: 1 = wait for a_ready before this chunk, 2 = last chunk of a
 // round (commit acc_full), 8 = first k-step overwrites D (start of a layer);
 // d_col = accumulator column offset inside the tile's 256-column TMEM region.
+template <bool PP>
 __device__ __forceinline__ void issuer_loop(const FusedChunk* __restrict__ chunks, int nchunks, int n_iter,
                                             uint8_t* smem, uint8_t* ring, uint32_t bar0,
                                             uint32_t tmem_base) {
-  uint32_t cnt = 0, a_cnt = 0;
-  const uint32_t a_addr0 = smem_u32(smem), a_addr1 = smem_u32(smem + kATileBytes);
+  uint32_t cnt = 0, a_cnt[2] = {0, 0};
+  const uint32_t a_addr[2] = {smem_u32(smem), smem_u32(smem + kATileBytes)};
   for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
-    for (int c = 0; c < nchunks; ++c, ++cnt) {
-      const FusedChunk ch = chunks[c];
-      if (ch.flags & 1) {
-        mbar_wait(bar0 + 8u * 8, a_cnt & 1);
-        ++a_cnt;
-        tc_fence_after_sync();
-      }
-      const uint32_t st = cnt % kRing;
-      mbar_wait(bar0 + 8u * st, (cnt / kRing) & 1);
-      tc_fence_after_sync();
-      const uint32_t idesc = idesc_bf16_f32(128, ch.npad);
-      const uint32_t w_addr = smem_u32(ring + st * kStageBytes);
-      const uint32_t lbo_b = (uint32_t)ch.npad * 16u;
+    for (int c0 = 0; c0 < nchunks;) {
+      const int c1 = PP ? round_end(chunks, c0, nchunks) : nchunks;
+      for (int rep = 0; rep < (PP ? 2 : 1); ++rep) {
+        for (int c = c0; c < c1; ++c, ++cnt) {
+          const FusedChunk ch = chunks[c];
+          if (ch.flags & 1) {
+            mbar_wait(bar_aready(bar0, PP ? rep : 0), a_cnt[PP ? rep : 0] & 1);
+            ++a_cnt[PP ? rep : 0];
+            tc_fence_after_sync();
+          }
+          const uint32_t st = cnt % kRing;
+          mbar_wait(bar0 + 8u * st, (cnt / kRing) & 1);
+          tc_fence_after_sync();
+          const uint32_t idesc = idesc_bf16_f32(128, ch.npad);
+          const uint32_t w_addr = smem_u32(ring + st * kStageBytes);
+          const uint32_t lbo_b = (uint32_t)ch.npad * 16u;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t aa = (t ? a_addr1 : a_addr0) + (uint32_t)ch.a_kgroup * 2048u;
-        for (int ks = 0; ks < ch.ksteps; ++ks) {
-          mma_bf16_ss(tmem_base + t * 256 + ch.d_col, smem_desc(aa + ks * 4096u, 2048u, 128u),
-                      smem_desc(w_addr + ks * 2u * lbo_b, lbo_b, 128u), idesc,
-                      ((ch.flags & 8) && ks == 0) ? 0u : 1u);
+          for (int t = 0; t < 2; ++t) {
+            if (PP && t != rep) continue;
+            const uint32_t aa = a_addr[t] + (uint32_t)ch.a_kgroup * 2048u;
+            for (int ks = 0; ks < ch.ksteps; ++ks) {
+              mma_bf16_ss(tmem_base + t * 256 + ch.d_col, smem_desc(aa + ks * 4096u, 2048u, 128u),
+                          smem_desc(w_addr + ks * 2u * lbo_b, lbo_b, 128u), idesc,
+                          ((ch.flags & 8) && ks == 0) ? 0u : 1u);
+            }
+          }
+          mma_commit(bar0 + 8u * (4 + st));
+          if (ch.flags & 2) mma_commit(bar_acc(bar0, PP ? rep : 0));
         }
       }
-      mma_commit(bar0 + 8u * (4 + st));
-      if (ch.flags & 2) mma_commit(bar0 + 8u * 9);
+      c0 = c1;
     }
   }
 }

@@ -53,19 +53,14 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
   uint8_t* ring = smem + 2 * kATileBytes;
   float* cst = reinterpret_cast<float*>(ring + kRing * kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(cst + kConstFloats);
-  // bars: [0..3] w_full, [4..7] w_empty, [8] a_ready, [9] acc_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  // bars: see fused_engine.cuh (ping-pong schedule: per-tile a_ready / acc_full)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
-  if (tid == 0) {
-    for (int i = 0; i < kRing; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), 1); }
-    mbar_init(BAR(8), 256);
-    mbar_init(BAR(9), 1);
-    mbar_fence_init();
-  }
+  if (tid == 0) init_barriers(bar0, /*pp=*/true);
   // constants -> smem
   {
     const float* prm = a.params;
@@ -101,9 +96,9 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
   const int nchunks = a.nchunks;
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop(chunks, nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<true>(chunks, nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 8) {
-    if ((tid & 31) == 0) issuer_loop(chunks, nchunks, n_iter, smem, ring, bar0, tmem_base);
+    if ((tid & 31) == 0) issuer_loop<true>(chunks, nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
     // ------------------------- row threads -------------------------
     const int tile = tid >> 7, r = tid & 127;
@@ -174,7 +169,7 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
         for (int g = 0; g < 14; ++g) store8(arow, 8 * g, xin + 8 * g);
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(BAR(8));
+        mbar_arrive(bar_aready(bar0, tile));
       }
 
       // ---- bilinear gather (fp32 maps, L2 resident); overlaps the first MMA ----
@@ -240,7 +235,7 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
       float f2[40];  // second half of the static per-view feature (src_feat * ref_feat)
       if (ST) {
         // ---- F1 epilogue: ELU(ray_dir_fc.0) -> A[256] ----
-        mbar_wait(BAR(9), acc_cnt & 1); ++acc_cnt;
+        mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
         tc_fence_after_sync();
 #pragma unroll 1
         for (int cb = 0; cb < 8; ++cb) {
@@ -250,9 +245,9 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(BAR(8));
+        mbar_arrive(bar_aready(bar0, tile));
         // ---- F2 epilogue: src_feat = ray_dir_fc.2 (35 of 48 cols), times ref_feat ----
-        mbar_wait(BAR(9), acc_cnt & 1); ++acc_cnt;
+        mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
         tc_fence_after_sync();
         float t16[16];
         tmem_ld32(tacc, acc);
@@ -314,10 +309,10 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(BAR(8));
+      mbar_arrive(bar_aready(bar0, tile));
 
       // ---- F3: ELU(base_fc.0) -> A[256] ----
-      mbar_wait(BAR(9), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
       tc_fence_after_sync();
 #pragma unroll 1
       for (int cb = 0; cb < 8; ++cb) {
@@ -327,10 +322,10 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(BAR(8));
+      mbar_arrive(bar_aready(bar0, tile));
 
       // ---- F4: x = ELU(base_fc.2); park x in TMEM cols [128,256); A = x * w1 ----
-      mbar_wait(BAR(9), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
       tc_fence_after_sync();
 #pragma unroll 1
       for (int cb = 0; cb < 4; ++cb) {
@@ -347,10 +342,10 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
       tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(BAR(8));
+      mbar_arrive(bar_aready(bar0, tile));
 
       // ---- F5: h = ELU(vis_fc.0); A = h; visibility logit = ELU(w_128 . h + b) ----
-      mbar_wait(BAR(9), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
       tc_fence_after_sync();
       float vlogit = cst[C_MISC + 0];
 #pragma unroll 1
@@ -368,10 +363,10 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
       const float vis1 = sigmoid_fast(elu_fast(vlogit)) * mask;  // mlp_network.py:272-274
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(BAR(8));
+      mbar_arrive(bar_aready(bar0, tile));
 
       // ---- F6: x += ELU(vis_fc.2[:128]); A = x * vis1 ----
-      mbar_wait(BAR(9), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
       tc_fence_after_sync();
 #pragma unroll 1
       for (int cb = 0; cb < 4; ++cb) {
@@ -395,10 +390,10 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
       tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(BAR(8));
+      mbar_arrive(bar_aready(bar0, tile));
 
       // ---- F7: vis2 = sigmoid(vis_fc2.2 . ELU(vis_fc2.0)) * mask ----
-      mbar_wait(BAR(9), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
       tc_fence_after_sync();
       float v2 = cst[C_MISC + 1];
 #pragma unroll 1
