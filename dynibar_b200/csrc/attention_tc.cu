@@ -1,0 +1,240 @@
+// Ray-transformer attention on tcgen05 (a11: ibrnet/mlp_network.py:13-31, :84-98).
+//
+// One CTA = one 128-row tile = 128/S whole rays (S | 128).  Q, K, V rows are
+// converted to bf16 and laid out as canonical K-major tiles in shared memory;
+// per head h:  logits = Q_h K_h^T  (UMMA 128x128x32, fp32 in TMEM columns [0,128))
+//              softmax over the keys of the row's own ray, in registers
+//              (query rows with <= 1 valid view attend uniformly: the reference
+//               masks QUERY rows, mlp_network.py:23-24, :91-94)
+//              O_h = P V_h        (UMMA 128x32x128; P is written back to smem as the
+//               A operand, V_h is read in place as an MN-major B operand)
+// O (fp32, TMEM columns [128,256)) is written to global at the end.
+#include "nets.cuh"
+#include "tc.cuh"
+
+namespace dyn {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kTile = 128 * 128 * 2;  // one bf16 [128 x 128] canonical tile: 32 KB
+constexpr int kQSlice = 128 * 32 * 2;  // Q_h: [128 x 32] = 8 KB
+// K, V, P tiles + Q_h slice + barriers/inv: 104 KB + 2.3 KB -> two CTAs per SM
+constexpr int kSmemAttn = 3 * kTile + kQSlice + 256 + 128 * 4 * 4;
+
+// idesc with B in MN-major layout (bit 16)
+__host__ __device__ constexpr uint32_t idesc_bf16_f32_bmn(int M, int N) {
+  return idesc_bf16_f32(M, N) | (1u << 16);
+}
+
+// Warp-cooperative load of this warp's 32 rows of a [*,128] fp32 matrix into the
+// canonical bf16 tile.  Per instruction pair a warp covers 8 rows x 32 columns:
+// lane l -> row (l % 8), k-group (l / 8): 128 contiguous bytes per row in global
+// memory, and the 8 lanes of every quarter-warp hit 8 different 16-byte rows of one
+// core matrix in shared memory (conflict-free STS.128).
+__device__ __forceinline__ void warp_rows_to_tile(uint8_t* tile, const float* __restrict__ src,
+                                                  long long row0, long long P, int warp, int lane) {
+#pragma unroll
+  for (int rg = 0; rg < 4; ++rg) {
+    const int r = warp * 32 + rg * 8 + (lane & 7);
+    const long long row = row0 + r;
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {
+      const int kg = kq * 4 + (lane >> 3);
+      uint4 q = make_uint4(0u, 0u, 0u, 0u);
+      if (row < P) {
+        const float4* s4 = reinterpret_cast<const float4*>(src + row * 128 + kg * 8);
+        const float4 a = __ldg(s4), b = __ldg(s4 + 1);
+        q.x = pack_bf16x2(a.x, a.y); q.y = pack_bf16x2(a.z, a.w);
+        q.z = pack_bf16x2(b.x, b.y); q.w = pack_bf16x2(b.z, b.w);
+      }
+      *reinterpret_cast<uint4*>(tile + kg * 2048 + (r >> 3) * 128 + (r & 7) * 16) = q;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 2)
+attention_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                    const float* __restrict__ nvalid, long long P, int S, float* __restrict__ O) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* kt = smem;
+  uint8_t* vt = smem + kTile;
+  uint8_t* pt = smem + 2 * kTile;
+  uint8_t* qt = smem + 3 * kTile;  // Q_h slice [128 x 32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kTile + kQSlice);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_s = smem_u32(bars), bar_o = smem_u32(bars + 1);
+  if (tid == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)(warp * 32), 0);
+
+  const int r = tid;
+  const size_t roff = (size_t)(r >> 3) * 128 + (r & 7) * 16;
+  const int ray_lo = (r / S) * S;  // first key row (inside the tile) of this row's ray
+  // key range touched by ANY row of this warp (tcgen05.ld is warp-collective: the
+  // column blocks a warp skips must be the same for all its lanes)
+  const int warp_lo = ((warp * 32) / S) * S;
+  const int warp_hi = ((warp * 32 + 31) / S + 1) * S;
+  const float scale = 0.17677669529663687f;  // 1 / sqrt(32)
+  uint32_t ph_s = 0, ph_o = 0;
+
+  const long long n_tiles = (P + 127) / 128;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row = tile * 128 + r;
+    const bool ok = row < P;
+    warp_rows_to_tile(kt, K, tile * 128, P, warp, tid & 31);
+    warp_rows_to_tile(vt, V, tile * 128, P, warp, tid & 31);
+    const bool q_valid = ok && nvalid[row] > 1.f;
+    // this row's Q_h (32 values) packed for head 0; later heads are prefetched during the softmax
+    uint4 qreg[4];
+    auto load_q = [&](int h) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        qreg[g] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) {
+          const float4* s4 = reinterpret_cast<const float4*>(Q + row * 128 + h * 32 + g * 8);
+          const float4 a = __ldg(s4), b = __ldg(s4 + 1);
+          qreg[g].x = pack_bf16x2(a.x, a.y); qreg[g].y = pack_bf16x2(a.z, a.w);
+          qreg[g].z = pack_bf16x2(b.x, b.y); qreg[g].w = pack_bf16x2(b.z, b.w);
+        }
+      }
+    };
+    load_q(0);
+    for (int h = 0; h < 4; ++h) {
+      // Q_h slice (the previous head's QK^T finished: every thread waited on bar_s)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(qt + roff + g * 2048) = qreg[g];
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+        const uint32_t idesc = idesc_bf16_f32(128, 128);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          mma_bf16_ss(tmem_base, smem_desc(smem_u32(qt) + (2 * ks) * 2048u, 2048u, 128u),
+                      smem_desc(smem_u32(kt) + (4 * h + 2 * ks) * 2048u, 2048u, 128u), idesc, ks ? 1u : 0u);
+        mma_commit(bar_s);
+      }
+      if (h < 3) load_q(h + 1);
+      mbar_wait(bar_s, ph_s & 1);
+      ++ph_s;
+      tc_fence_after_sync();
+      // ---- softmax over this row's ray (keys [ray_lo, ray_lo + S)) ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cb = 0; cb < 128; cb += 32) {
+        if (cb + 32 <= warp_lo || cb >= warp_hi) continue;
+        float l[32];
+        tmem_ld32(tacc + cb, l);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int key = cb + i;
+          if (key >= ray_lo && key < ray_lo + S) mx = fmaxf(mx, q_valid ? l[i] * scale : 0.f);
+        }
+      }
+      float den = 0.f;
+      // previous head's P V must be done before P is overwritten
+      if (h > 0) { mbar_wait(bar_o, ph_o & 1); ++ph_o; tc_fence_after_sync(); }
+#pragma unroll 1
+      for (int cb = 0; cb < 128; cb += 32) {
+        float p[32];
+        const bool any = !(cb + 32 <= warp_lo || cb >= warp_hi);
+        if (any) {
+          tmem_ld32(tacc + cb, p);
+          tmem_wait_ld();
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int key = cb + i;
+          float e = 0.f;
+          if (any && key >= ray_lo && key < ray_lo + S) e = q_valid ? __expf(p[i] * scale - mx) : 1.f;
+          p[i] = e;
+          den += e;
+        }
+        // unnormalised probabilities -> bf16 A operand (normalisation folded into the output)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 q;
+          q.x = pack_bf16x2(p[8 * g], p[8 * g + 1]); q.y = pack_bf16x2(p[8 * g + 2], p[8 * g + 3]);
+          q.z = pack_bf16x2(p[8 * g + 4], p[8 * g + 5]); q.w = pack_bf16x2(p[8 * g + 6], p[8 * g + 7]);
+          *reinterpret_cast<uint4*>(pt + roff + ((cb >> 3) + g) * 2048) = q;
+        }
+      }
+      const float inv = 1.f / den;
+      // O_h needs 1/den per row: stash it in registers via a small array indexed by h
+      // (written out in the final pass) -> keep as 4 scalars
+      if (h == 0) reinterpret_cast<float*>(bars + 8)[r * 4 + 0] = inv;
+      if (h == 1) reinterpret_cast<float*>(bars + 8)[r * 4 + 1] = inv;
+      if (h == 2) reinterpret_cast<float*>(bars + 8)[r * 4 + 2] = inv;
+      if (h == 3) reinterpret_cast<float*>(bars + 8)[r * 4 + 3] = inv;
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+        const uint32_t idesc = idesc_bf16_f32_bmn(128, 32);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          mma_bf16_ss(tmem_base + 128 + 32 * h, smem_desc(smem_u32(pt) + ks * 4096u, 2048u, 128u),
+                      // V_h as MN-major B: n = d in [32h, 32h+32) -> n-groups at stride 2048 (SBO),
+                      // k = key -> k-groups at stride 128 (LBO); this k-step covers keys [16ks, 16ks+16)
+                      smem_desc(smem_u32(vt) + (4 * h) * 2048u + ks * 256u, 128u, 2048u), idesc,
+                      ks ? 1u : 0u);
+        mma_commit(bar_o);
+      }
+    }
+    mbar_wait(bar_o, ph_o & 1);
+    ++ph_o;
+    tc_fence_after_sync();
+    const float* invs = reinterpret_cast<const float*>(bars + 8) + r * 4;
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      float o[32];
+      tmem_ld32(tacc + 128 + 32 * h, o);
+      tmem_wait_ld();
+      if (ok) {
+        const float inv = invs[h];
+        float4* dst = reinterpret_cast<float4*>(O + row * 128 + 32 * h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+      }
+    }
+    tc_fence_before_sync();
+    __syncthreads();  // tiles + TMEM are reused by the next iteration
+  }
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace
+
+bool attention_tc_supported(int S) { return S >= 1 && S <= 128 && (128 % S) == 0; }
+
+int launch_attention_tc(const float* Q, const float* K, const float* V, const float* nvalid, long long P,
+                        int S, float* O, cudaStream_t st) {
+  if (P == 0) return DYN_OK;
+  int dev = 0, sms = 148;
+  DYN_CUDA(cudaGetDevice(&dev));
+  DYN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long n_tiles = (P + 127) / 128;
+  const int grid = (int)(n_tiles < 2 * sms ? n_tiles : 2 * sms);
+  const int smem = kSmemAttn;
+  DYN_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ProfScope prof(PROF_ATTENTION, st);
+  attention_tc_kernel<<<grid, 128, smem, st>>>(Q, K, V, nvalid, P, S, O);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
+}  // namespace dyn

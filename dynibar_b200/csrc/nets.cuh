@@ -31,6 +31,10 @@ int net_dynamic_fused(const dyn_net* n, const float* pts, const float* pts_seq, 
 int debug_point_chain(const dyn_net* n, const float* G, const float* nvalid, const float* pts,
                       const float* ray_dir, int R, int S, float* g2, float* Q, float* K, float* V,
                       float* O, float* out_a, float* out_b, float* posenc_ws, cudaStream_t st);
+// tcgen05 ray-transformer attention (attention_tc.cu); S must divide 128
+bool attention_tc_supported(int S);
+int launch_attention_tc(const float* Q, const float* K, const float* V, const float* nvalid, long long P,
+                        int S, float* O, cudaStream_t st);
 int zero_last_samples(float* coeff, int R, int S, int width, cudaStream_t st);
 
 }  // namespace dyn

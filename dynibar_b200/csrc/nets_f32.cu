@@ -864,7 +864,9 @@ static int run_point_fused(const dyn_net* n, const float* G, long long P, int R,
     p1.posenc = posenc_tab;
   }
   RUN(launch_point1_fused(n, p1, st));
-  {
+  if (attention_tc_supported(S)) {
+    RUN(launch_attention_tc(t.Q, t.K, t.V, t.nvalid, P, S, t.O, st));
+  } else {
     int threads = ((S + 31) / 32) * 32;
     size_t smem = (size_t)2 * S * 32 * sizeof(float);
     if (threads > 1024) return fail(DYN_E_INVALID, "ray transformer supports S <= 1024 (got %d)", S);

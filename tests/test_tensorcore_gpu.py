@@ -134,7 +134,7 @@ def test_fused_view_stage_matches_staged(golden, name):
 
 
 @pytest.mark.parametrize("kind", ["dynamic", "static"])
-@pytest.mark.parametrize("S", [64, 128, 20])
+@pytest.mark.parametrize("S", [64, 128, 20, 16, 32])
 def test_fused_point_stage(kind, S):
   """point1 (geometry_fc, Q|K|V) -> attention -> point2 (fc + LayerNorm + heads) on random
   pooled features, against the oracle's formulas with bf16 GEMM operands."""
