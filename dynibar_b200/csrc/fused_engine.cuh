@@ -116,11 +116,12 @@ __device__ __forceinline__ void rs_step(const float* in, float* out, bool upper,
 __device__ __forceinline__ uint32_t bar_aready(uint32_t bar0, int tile) { return bar0 + 8u * (8 + 2 * tile); }
 __device__ __forceinline__ uint32_t bar_acc(uint32_t bar0, int tile) { return bar0 + 8u * (9 + 2 * tile); }
 
-__device__ __forceinline__ void init_barriers(uint32_t bar0, bool pp) {
+// `arrivals` = row threads per 128-row tile (128, or 256 in the twin-warp kernels)
+__device__ __forceinline__ void init_barriers(uint32_t bar0, bool pp, int arrivals = 128) {
   for (int i = 0; i < kRing; ++i) { mbar_init(bar0 + 8u * i, 1); mbar_init(bar0 + 8u * (4 + i), 1); }
-  mbar_init(bar_aready(bar0, 0), pp ? 128 : 256);
+  mbar_init(bar_aready(bar0, 0), pp ? arrivals : 2 * arrivals);
   mbar_init(bar_acc(bar0, 0), 1);
-  mbar_init(bar_aready(bar0, 1), 128);
+  mbar_init(bar_aready(bar0, 1), arrivals);
   mbar_init(bar_acc(bar0, 1), 1);
   mbar_fence_init();
 }
@@ -159,9 +160,9 @@ __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chu
 template <bool PP>
 __device__ __forceinline__ void issuer_loop(const FusedChunk* __restrict__ chunks, int nchunks, int n_iter,
                                             uint8_t* smem, uint8_t* ring, uint32_t bar0,
-                                            uint32_t tmem_base) {
+                                            uint32_t tmem_base, int a_tile_bytes = kATileBytes) {
   uint32_t cnt = 0, a_cnt[2] = {0, 0};
-  const uint32_t a_addr[2] = {smem_u32(smem), smem_u32(smem + kATileBytes)};
+  const uint32_t a_addr[2] = {smem_u32(smem), smem_u32(smem + a_tile_bytes)};
   for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
     for (int c0 = 0; c0 < nchunks;) {
       const int c1 = PP ? round_end(chunks, c0, nchunks) : nchunks;

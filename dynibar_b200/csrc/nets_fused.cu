@@ -23,6 +23,8 @@
 //
 // Reference semantics: ibrnet/projection.py:103-176, ibrnet/mlp_network.py:236-284
 // (dynamic) and :423-497 (static).
+#include <stdlib.h>
+
 #include "fused_engine.cuh"
 #include "geometry.cuh"
 #include "nets.cuh"
@@ -550,6 +552,16 @@ int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
     a.o_b5 = L.vis0.b; a.o_b6 = L.vis2.b; a.o_w6 = L.vis2.w; a.o_b7 = L.vis2_0.b;
     a.o_w8 = L.vis2_2.w; a.o_b8 = L.vis2_2.b; a.o_s = -1;
     a.anti_alias = 0; a.mask_rgb = 0;
+  }
+  {
+    // default: twin-warp kernel (16 row warps per SM); DYN_VIEW_TWIN=0 selects the
+    // one-thread-per-row kernel below (kept for A/B measurements)
+    static int use_twin = -1;
+    if (use_twin < 0) {
+      const char* e = getenv("DYN_VIEW_TWIN");
+      use_twin = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_twin && n->twin.img != nullptr) return launch_view_twin(n, a, V, st);
   }
   int dev = 0, sms = 148;
   DYN_CUDA(cudaGetDevice(&dev));

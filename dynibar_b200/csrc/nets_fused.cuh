@@ -116,6 +116,11 @@ int launch_point1_fused(const dyn_net* n, Point1Args& a, cudaStream_t st);
 int launch_point2_fused(const dyn_net* n, Point2Args& a, cudaStream_t st);
 int launch_rgbhead_fused(const dyn_net* n, RgbHeadArgs& a, cudaStream_t st);
 
+// twin-warp per-view stage (view_twin.cu)
+size_t view_twin_bytes(int kind);
+int view_twin_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes, cudaStream_t st);
+int launch_view_twin(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st);
+
 size_t fused_view_bytes(int kind);
 int fused_view_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes,
                      cudaStream_t st);

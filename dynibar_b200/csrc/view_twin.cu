@@ -1,0 +1,612 @@
+// Twin-warp version of the fused per-(point, view) stage (see nets_fused.cu for the
+// single-warp-per-row version and the math; reference: ibrnet/projection.py:103-176,
+// ibrnet/mlp_network.py:236-284 / :423-497).
+//
+// Same engine (persistent CTA, two 128-row UMMA tiles, ping-pong MMA schedule,
+// weight ring), but every row is served by TWO threads in twin warps w and w+8
+// (same TMEM lane quadrant): 16 row warps per SM instead of 8, which is what the
+// latency-bound epilogues need.  Each twin owns half of every layer's output
+// columns and half of the gathered / pooled channels; the twins exchange only two
+// scalars per row and iteration (the partial visibility logits).
+//
+//   warps 0-7  : twin 0 of rows (tile = w >> 2, quadrant = w & 3)
+//   warps 8-15 : twin 1 of the same rows
+//   warp 16    : MMA issuer        warp 17 : weight producer
+#include "fused_engine.cuh"
+#include "geometry.cuh"
+#include "nets.cuh"
+
+namespace dyn {
+
+using namespace tc;
+using namespace fe;
+
+namespace {
+
+constexpr int kTwinATile = 65536;  // K <= 256 in the per-view nets: 32 k-groups
+constexpr int T_B1 = 0, T_B2 = 256, T_B3 = 304, T_B4 = 560, T_B5 = 688, T_B6 = 816, T_W6V = 944,
+              T_B7 = 1072, T_W8 = 1200, T_MISC = 1328, T_DFEAT = 1344, T_XCH = 1408;  // + 2 x 256 exchange
+constexpr int kTwinConst = T_XCH + 1024;
+constexpr int kSmemTwin = 2 * kTwinATile + kRing * kStageBytes + kTwinConst * 4 + 256;
+
+__device__ __forceinline__ void pair_sync(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+
+// 11 values of one PE component: [x, cos(2^k x) k=0..4, sin(2^k x) k=0..4]
+__device__ __forceinline__ void pe_comp(float x, float* o) {
+  float s, c;
+  __sincosf(x, &s, &c);
+  o[0] = x;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    o[1 + k] = c;
+    o[6 + k] = s;
+    const float s2 = 2.f * s * c, c2 = 1.f - 2.f * s * s;
+    s = s2; c = c2;
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void elu_block_to_A(uint8_t* arow, uint32_t tacc, int col0, const float* bias) {
+#pragma unroll 1
+  for (int cb = 0; cb < N; cb += 32) {
+    float acc[32];
+    tmem_ld32(tacc + col0 + cb, acc);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = elu_fast(acc[i] + bias[col0 + cb + i]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) store8(arow, col0 + cb + 8 * g, acc + 8 * g);
+  }
+}
+
+template <int VP, bool ST>
+__global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant__ ViewFusedArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem + 2 * kTwinATile;
+  float* cst = reinterpret_cast<float*>(ring + kRing * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cst + kTwinConst);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar0 = smem_u32(bars);
+
+  if (tid == 0) init_barriers(bar0, /*pp=*/true, /*arrivals=*/256);
+  {
+    const float* prm = a.params;
+    for (int i = tid; i < 256; i += blockDim.x) {
+      if (ST) cst[T_B1 + i] = prm[a.o_b1 + i];
+      cst[T_B3 + i] = prm[a.o_b3 + i];
+    }
+    for (int i = tid; i < 128; i += blockDim.x) {
+      cst[T_B4 + i] = prm[a.o_b4 + i];
+      cst[T_B5 + i] = prm[a.o_b5 + i];
+      cst[T_B6 + i] = prm[a.o_b6 + i];
+      cst[T_W6V + i] = prm[a.o_w6 + 128 * 128 + i];
+      cst[T_B7 + i] = prm[a.o_b7 + i];
+      cst[T_W8 + i] = prm[a.o_w8 + i];
+    }
+    if (tid < 48) cst[T_B2 + tid] = (ST && tid < kF) ? prm[a.o_b2 + tid] : 0.f;
+    if (tid < 40) cst[T_DFEAT + tid] = (!ST && tid < kF) ? a.dfeat[tid] : 0.f;
+    if (tid == 0) {
+      cst[T_MISC + 0] = prm[a.o_b6 + 128];
+      cst[T_MISC + 1] = prm[a.o_b8];
+      cst[T_MISC + 2] = (ST && a.o_s >= 0) ? fabsf(prm[a.o_s]) : 0.f;
+    }
+  }
+  if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long n_rows = a.P * VP;
+  const int n_iter = (int)((n_rows + 255) / 256);
+
+  if (warp == 17) {
+    if ((tid & 31) == 0) producer_loop<true>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
+  } else if (warp == 16) {
+    if ((tid & 31) == 0)
+      issuer_loop<true>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kTwinATile);
+  } else {
+    const int tw = tid >> 8;           // twin index
+    const int t = tid & 255;           // row slot inside the 256-row iteration
+    const int tile = t >> 7, r = t & 127;
+    uint8_t* arow = smem + tile * kTwinATile + (r >> 3) * 128 + (r & 7) * 16;
+    const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(tile * 256));
+    const int v = t % VP;
+    const int gl = t & (VP - 1);
+    const int pair = warp & 7;
+    float* xch5 = cst + T_XCH;        // [2][256] partial visibility logits of vis_fc
+    float* xch7 = cst + T_XCH + 512;  // [2][256] partial logits of vis_fc2
+    uint32_t acc_cnt = 0;
+    const float wh = a.w_img, hh = a.h_img;
+    constexpr int NG = ST ? 5 : (0);  // static: 5 channel groups per twin (set below for dynamic)
+    (void)NG;
+
+    for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
+      const long long pl = ((long long)it * 256 + t) / VP;
+      const bool pt_ok = pl < a.P;
+      const bool valid = pt_ok && v < a.V;
+      const long long m = pl * a.V + v;
+      const long long ray = pt_ok ? pl / a.S : 0;
+
+      // ---- geometry (both twins; cheap) ----
+      float p3[3] = {0.f, 0.f, 0.f}, q3[3];
+      if (pt_ok) { p3[0] = a.pts[pl * 3]; p3[1] = a.pts[pl * 3 + 1]; p3[2] = a.pts[pl * 3 + 2]; }
+      q3[0] = p3[0]; q3[1] = p3[1]; q3[2] = p3[2];
+      if (!ST && valid) {
+        const float* q = a.pts_seq + ((long long)v * a.seq_stride + pl) * 3;
+        q3[0] = q[0]; q3[1] = q[1]; q3[2] = q[2];
+      }
+      const int vc = valid ? v : 0;
+      float pu, pv;
+      bool front;
+      project_point(a.cams.P[vc], q3[0], q3[1], q3[2], pu, pv, front);
+      const bool inb = (pu <= wh - 1.f) && (pu >= 0.f) && (pv <= hh - 1.f) && (pv >= 0.f);
+      const float mask_proj = (valid && inb && front) ? 1.f : 0.f;
+      float rd[4];
+      {
+        float a0 = a.cams.tgt[0] - p3[0], a1 = a.cams.tgt[1] - p3[1], a2 = a.cams.tgt[2] - p3[2];
+        normalize3(a0, a1, a2);
+        float b0 = a.cams.center[vc][0] - q3[0], b1 = a.cams.center[vc][1] - q3[1],
+              b2 = a.cams.center[vc][2] - q3[2];
+        normalize3(b0, b1, b2);
+        rd[0] = a0 - b0; rd[1] = a1 - b1; rd[2] = a2 - b2;
+        rd[3] = a0 * b0 + a1 * b1 + a2 * b2;
+        normalize3(rd[0], rd[1], rd[2]);
+      }
+
+      if (ST) {
+        // ---- layer-1 operand, 56 columns per twin (component-major PE, see view_twin_build) ----
+        float pl6[6];
+        {
+          const float ox = a.cams.center[vc][0], oy = a.cams.center[vc][1], oz = a.cams.center[vc][2];
+          float dx = p3[0] - ox, dy = p3[1] - oy, dz = p3[2] - oz;
+          normalize3(dx, dy, dz);
+          pl6[0] = dx; pl6[1] = dy; pl6[2] = dz;
+          pl6[3] = oy * dz - oz * dy;
+          pl6[4] = oz * dx - ox * dz;
+          pl6[5] = ox * dy - oy * dx;
+        }
+        float xin[56];
+        if (tw == 0) {
+          pe_comp(p3[0], xin); pe_comp(p3[1], xin + 11); pe_comp(p3[2], xin + 22);
+          pe_comp(pl6[0], xin + 33); pe_comp(pl6[1], xin + 44);
+          xin[55] = 0.f;
+        } else {
+          pe_comp(pl6[2], xin); pe_comp(pl6[3], xin + 11); pe_comp(pl6[4], xin + 22);
+          pe_comp(pl6[5], xin + 33);
+          xin[44] = rd[0]; xin[45] = rd[1]; xin[46] = rd[2]; xin[47] = rd[3];
+#pragma unroll
+          for (int i = 48; i < 56; ++i) xin[i] = 0.f;
+        }
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 56; ++i) xin[i] = 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < 7; ++g) store8(arow, 56 * tw + 8 * g, xin + 8 * g);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(bar_aready(bar0, tile));
+      }
+
+      // ---- gather: rgb (both twins) + this twin's 16 feature channels ----
+      float chv[40];  // this twin's pooled channels (layout in view_twin_build)
+#pragma unroll
+      for (int i = 0; i < 40; ++i) chv[i] = 0.f;
+      float rgb[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+        const float gx = 2.f * pu / (wh - 1.f) - 1.f, gy = 2.f * pv / (hh - 1.f) - 1.f;
+        {
+          const float fx = (gx + 1.f) * 0.5f * (float)(a.w - 1), fy = (gy + 1.f) * 0.5f * (float)(a.h - 1);
+          const float x0f = floorf(fx), y0f = floorf(fy);
+          const int x0 = (int)x0f, y0 = (int)y0f;
+          const float ax = fx - x0f, ay = fy - y0f, bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
+          const float* base = a.feat_cl + (long long)v * a.h * a.w * kC + 16 * tw;
+          const int fo = tw == 0 ? 3 : 0;  // twin 0 keeps rgb in slots 0..2
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const int xi = x0 + dx, yi = y0 + dy;
+              const float wgt = (dx ? ax : bx) * (dy ? ay : by);
+              if (xi >= 0 && xi < a.w && yi >= 0 && yi < a.h) {
+                const float4* tp = reinterpret_cast<const float4*>(base + ((long long)yi * a.w + xi) * kC);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 q = __ldg(tp + j);
+                  if (tw == 0) {
+                    chv[3 + 4 * j] += q.x * wgt; chv[4 + 4 * j] += q.y * wgt;
+                    chv[5 + 4 * j] += q.z * wgt; chv[6 + 4 * j] += q.w * wgt;
+                  } else {
+                    chv[4 * j] += q.x * wgt; chv[1 + 4 * j] += q.y * wgt;
+                    chv[2 + 4 * j] += q.z * wgt; chv[3 + 4 * j] += q.w * wgt;
+                  }
+                }
+              }
+            }
+          (void)fo;
+        }
+        {
+          const float fx = (gx + 1.f) * 0.5f * (float)(a.W - 1), fy = (gy + 1.f) * 0.5f * (float)(a.H - 1);
+          const float x0f = floorf(fx), y0f = floorf(fy);
+          const int x0 = (int)x0f, y0 = (int)y0f;
+          const float ax = fx - x0f, ay = fy - y0f, bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
+          const float* base = a.rgbs + (long long)v * a.H * a.W * 3;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const int xi = x0 + dx, yi = y0 + dy;
+              const float wgt = (dx ? ax : bx) * (dy ? ay : by);
+              if (xi >= 0 && xi < a.W && yi >= 0 && yi < a.H) {
+                const float* tp = base + ((long long)yi * a.W + xi) * 3;
+                rgb[0] += __ldg(tp) * wgt; rgb[1] += __ldg(tp + 1) * wgt; rgb[2] += __ldg(tp + 2) * wgt;
+              }
+            }
+        }
+      }
+      float mask = mask_proj;
+      if (ST && a.mask_rgb) mask *= ((rgb[0] + rgb[1] + rgb[2]) > 1e-3f) ? 1.f : 0.f;
+      if (tw == 0) {
+        chv[0] = rgb[0]; chv[1] = rgb[1]; chv[2] = rgb[2];
+        if (valid) {
+          a.mask_proj[m] = mask_proj;
+          if (ST) {
+            a.mask_eff[m] = mask;
+            reinterpret_cast<float4*>(a.ray_diff)[m] = make_float4(rd[0], rd[1], rd[2], rd[3]);
+            a.rgb_in[m * 3] = rgb[0]; a.rgb_in[m * 3 + 1] = rgb[1]; a.rgb_in[m * 3 + 2] = rgb[2];
+          }
+        }
+      }
+
+      if (ST) {
+        // ---- F1 epilogue: this twin's 128 of the 256 columns ----
+        mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+        tc_fence_after_sync();
+        elu_block_to_A<128>(arow, tacc, 128 * tw, cst + T_B1);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(bar_aready(bar0, tile));
+        // ---- F2: src_feat (35 of 48 columns) * ref_feat; twin 0 keeps 0..17, twin 1 keeps 18..34 ----
+        mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+        tc_fence_after_sync();
+        float s48[48];
+        tmem_ld32(tacc, s48);
+        tmem_ld16(tacc + 32, s48 + 32);
+        tmem_wait_ld();
+        const float* rf = a.ref_feat + ray * kF;
+        if (tw == 0) {
+#pragma unroll
+          for (int i = 0; i < 18; ++i) chv[19 + i] = valid ? (s48[i] + cst[T_B2 + i]) * __ldg(rf + i) : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 17; ++i)
+            chv[16 + i] = valid ? (s48[18 + i] + cst[T_B2 + 18 + i]) * __ldg(rf + 18 + i) : 0.f;
+        }
+      } else {
+        // dynamic: + time feature on this twin's channels (mlp_network.py:244-247)
+        if (tw == 0) {
+#pragma unroll
+          for (int i = 0; i < 19; ++i) chv[i] = valid ? chv[i] + cst[T_DFEAT + i] : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) chv[i] = valid ? chv[i] + cst[T_DFEAT + 19 + i] : 0.f;
+        }
+      }
+
+      // ---- pooling weights (both twins) ----
+      float w1;
+      if (ST && a.anti_alias) {
+        const float e = ex2f(cst[T_MISC + 2] * (rd[3] - 1.f) * 1.4426950408889634f);
+        const float emin = group_min<VP>(valid ? e : INFINITY);
+        w1 = valid ? (e - emin) * mask : 0.f;
+      } else {
+        w1 = mask;
+      }
+      w1 = w1 / (group_sum<VP>(w1) + 1e-8f);
+
+      // ---- first pooling on this twin's channel groups: [mean8 | var8 | feat8] per group ----
+      {
+        constexpr int ng0 = ST ? 5 : 3, ng1 = ST ? 5 : 2;
+        const int col_base = tw == 0 ? 0 : 24 * ng0;
+#pragma unroll
+        for (int g = 0; g < ng0; ++g) {
+          if (tw == 1 && g >= ng1) break;
+          float o[24];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float fv = chv[8 * g + j];
+            const float s1 = group_sum<VP>(w1 * fv);
+            const float d = fv - s1;
+            const float s2 = group_sum<VP>(w1 * d * d);
+            o[j] = s1; o[8 + j] = s2; o[16 + j] = fv;
+          }
+          store8(arow, col_base + 24 * g, o);
+          store8(arow, col_base + 24 * g + 8, o + 8);
+          store8(arow, col_base + 24 * g + 16, o + 16);
+        }
+        if (!ST && tw == 1) {  // dynamic: zero the K padding 120..127
+          float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          store8(arow, 120, z);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(bar_aready(bar0, tile));
+
+      // ---- F3: ELU(base_fc.0), this twin's 128 columns ----
+      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+      tc_fence_after_sync();
+      elu_block_to_A<128>(arow, tacc, 128 * tw, cst + T_B3);
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(bar_aready(bar0, tile));
+
+      const int c0 = 64 * tw;  // this twin's columns of the 128-wide layers
+      // ---- F4: x = ELU(base_fc.2) -> TMEM [128,256); A = x * w1 ----
+      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int cb = c0; cb < c0 + 64; cb += 32) {
+        float acc[32];
+        tmem_ld32(tacc + cb, acc);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = elu_fast(acc[i] + cst[T_B4 + cb + i]);
+        tmem_st32(tacc + 128 + cb, acc);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] *= w1;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
+      }
+      tmem_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(bar_aready(bar0, tile));
+
+      // ---- F5: h = ELU(vis_fc.0) -> A; partial visibility logit ----
+      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+      tc_fence_after_sync();
+      {
+        float part = 0.f;
+#pragma unroll 1
+        for (int cb = c0; cb < c0 + 64; cb += 32) {
+          float acc[32];
+          tmem_ld32(tacc + cb, acc);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            acc[i] = elu_fast(acc[i] + cst[T_B5 + cb + i]);
+            part = fmaf(acc[i], cst[T_W6V + cb + i], part);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
+        }
+        xch5[tw * 256 + t] = part;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(bar_aready(bar0, tile));
+
+      // ---- F6: x += ELU(vis_fc.2[:128]); A = x * vis1 ----
+      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+      tc_fence_after_sync();
+      // both twins arrived on a_ready before this MMA ran: the partial logits are visible
+      const float vlogit = cst[T_MISC + 0] + xch5[t] + xch5[256 + t];
+      const float vis1 = sigmoid_fast(elu_fast(vlogit)) * mask;
+#pragma unroll 1
+      for (int cb = c0; cb < c0 + 64; cb += 32) {
+        float acc[32], xs[32];
+        tmem_ld32(tacc + cb, acc);
+        tmem_ld32(tacc + 128 + cb, xs);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xs[i] += elu_fast(acc[i] + cst[T_B6 + cb + i]);
+        tmem_st32(tacc + 128 + cb, xs);
+        if (ST && valid) {
+          float4* xo = reinterpret_cast<float4*>(a.X + m * 128 + cb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xo[i] = make_float4(xs[4 * i], xs[4 * i + 1], xs[4 * i + 2], xs[4 * i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xs[i] *= vis1;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, xs + 8 * g);
+      }
+      tmem_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(bar_aready(bar0, tile));
+
+      // ---- F7: vis2 = sigmoid(vis_fc2.2 . ELU(vis_fc2.0)) * mask ----
+      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+      tc_fence_after_sync();
+      {
+        float part = 0.f;
+#pragma unroll 1
+        for (int cb = c0; cb < c0 + 64; cb += 32) {
+          float acc[32];
+          tmem_ld32(tacc + cb, acc);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            part = fmaf(elu_fast(acc[i] + cst[T_B7 + cb + i]), cst[T_W8 + cb + i], part);
+        }
+        xch7[tw * 256 + t] = part;
+      }
+      pair_sync(pair);
+      const float v2 = cst[T_MISC + 1] + xch7[t] + xch7[256 + t];
+      const float vis2 = sigmoid_fast(v2) * mask;
+      if (ST && valid && tw == 0) a.vis2[m] = vis2;
+      const float vsum = group_sum<VP>(vis2);
+      const float w2 = vis2 / (vsum + 1e-8f);
+      const float W = group_sum<VP>(w2);
+      const float nval = group_sum<VP>(mask);
+
+      // ---- second pooling on this twin's 64 channels: reduce-scatter of sum(w x), sum(w x^2) ----
+      {
+        const bool b0 = gl & 1, b1 = gl & 2, b2 = gl & 4, b3 = gl & 8;
+        constexpr int NO = VP == 16 ? 4 : 8;
+        const int cbase = c0 + (b0 ? 32 : 0) + (b1 ? 16 : 0) + (b2 ? 8 : 0) + ((VP == 16 && b3) ? 4 : 0);
+        float mean[NO], sq[NO];
+        float lo[32], hi[32];
+        tmem_ld32(tacc + 128 + c0, lo);
+        tmem_ld32(tacc + 128 + c0 + 32, hi);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float s1[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float l = q ? w2 * lo[i] * lo[i] : w2 * lo[i];
+            const float h = q ? w2 * hi[i] * hi[i] : w2 * hi[i];
+            const float send = b0 ? l : h, keep = b0 ? h : l;
+            s1[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+          float s2[16], s3[8];
+          rs_step<32>(s1, s2, b1, 2);
+          rs_step<16>(s2, s3, b2, 4);
+          float* dst = q ? sq : mean;
+          if (VP == 16) {
+            float s4[4];
+            rs_step<8>(s3, s4, b3, 8);
+#pragma unroll
+            for (int i = 0; i < NO; ++i) dst[i] = s4[i < 4 ? i : 0];
+          } else {
+#pragma unroll
+            for (int i = 0; i < NO; ++i) dst[i] = s3[i < 8 ? i : 0];
+          }
+        }
+        if (pt_ok) {
+          float* g = a.G + pl * kGStride;
+#pragma unroll
+          for (int i = 0; i < NO; ++i) {
+            const float mu = mean[i];
+            g[cbase + i] = mu;
+            g[128 + cbase + i] = sq[i] - mu * mu * (2.f - W);
+          }
+          if (gl == 0 && tw == 0) {
+            g[256] = W / (float)a.V;
+            a.nvalid[pl] = nval;
+          }
+        }
+      }
+      tc_fence_before_sync();
+    }
+  }
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// host: weight images in the twin column layouts
+// ---------------------------------------------------------------------------
+size_t view_twin_bytes(int kind) { (void)kind; return (size_t)(512 * 1024); }
+
+int view_twin_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes, cudaStream_t st) {
+  std::vector<uint8_t> img;
+  std::vector<FusedChunk> tab;
+  auto add = [&](const LinearP& l, int N, int Npad, int Kpad, std::vector<int> map) {
+    HostLayer L;
+    L.W = P + l.w; L.N = N; L.Kw = l.in; L.Npad = Npad; L.Kpad = Kpad; L.colmap = std::move(map);
+    append_layer(L, img, tab);
+  };
+  if (n->kind == DYN_NET_STATIC) {
+    const StaticLayout& L = n->sl;
+    // layer 1: component-major PE; twin 0 = comps 0..4 (+1 pad), twin 1 = comps 5..8, ray_diff, pad
+    std::vector<int> m1(112, -1);
+    auto comp_col = [](int ci, int j) {  // j: 0 = x, 1..5 = cos f_k, 6..10 = sin f_k
+      if (ci < 3) return j == 0 ? ci : (j <= 5 ? 3 + 3 * (j - 1) + ci : 18 + 3 * (j - 6) + ci);
+      const int d = ci - 3;
+      return j == 0 ? 33 + d : (j <= 5 ? 39 + 6 * (j - 1) + d : 69 + 6 * (j - 6) + d);
+    };
+    for (int ci = 0; ci < 5; ++ci)
+      for (int j = 0; j < 11; ++j) m1[11 * ci + j] = comp_col(ci, j);
+    for (int ci = 5; ci < 9; ++ci)
+      for (int j = 0; j < 11; ++j) m1[56 + 11 * (ci - 5) + j] = comp_col(ci, j);
+    for (int i = 0; i < 4; ++i) m1[100 + i] = 99 + i;
+    add(L.ray_dir0, 256, 256, 112, m1);
+    add(L.ray_dir2, kF, 48, 256, identity_map(256, 256));
+    // layer 3: per twin 5 groups of [mean8 | var8 | feat8]; concat channel c: mean c, var 70+c, feat 140+c
+    std::vector<int> m3(240, -1);
+    auto chan = [](int tw, int slot) {  // concat channel (0..69) of a twin's slot, -1 = pad
+      if (tw == 0) return slot < 19 ? slot : (slot < 37 ? 35 + (slot - 19) : -1);
+      return slot < 16 ? 19 + slot : (slot < 33 ? 53 + (slot - 16) : -1);
+    };
+    for (int tw = 0; tw < 2; ++tw)
+      for (int s = 0; s < 40; ++s) {
+        const int c = chan(tw, s);
+        if (c < 0) continue;
+        const int base = 120 * tw + 24 * (s / 8) + (s % 8);
+        m3[base] = c; m3[base + 8] = 70 + c; m3[base + 16] = 140 + c;
+      }
+    add(L.base0, 256, 256, 240, m3);
+    add(L.base2, 128, 128, 256, identity_map(256, 256));
+    add(L.vis0, 128, 128, 128, identity_map(128, 128));
+    add(L.vis2, 128, 128, 128, identity_map(128, 128));
+    add(L.vis2_0, 128, 128, 128, identity_map(128, 128));
+  } else {
+    const DynamicLayout& L = n->dl;
+    // twin 0: channels 0..18 (3 groups, cols 0..71), twin 1: channels 19..34 (2 groups, cols 72..119)
+    std::vector<int> m3(128, -1);
+    for (int s = 0; s < 24; ++s)
+      if (s < 19) { const int b = 24 * (s / 8) + (s % 8); m3[b] = s; m3[b + 8] = 35 + s; m3[b + 16] = 70 + s; }
+    for (int s = 0; s < 16; ++s) {
+      const int c = 19 + s, b = 72 + 24 * (s / 8) + (s % 8);
+      m3[b] = c; m3[b + 8] = 35 + c; m3[b + 16] = 70 + c;
+    }
+    add(L.base0, 256, 256, 128, m3);
+    add(L.base2, 128, 128, 256, identity_map(256, 256));
+    add(L.vis0, 128, 128, 128, identity_map(128, 128));
+    add(L.vis2, 128, 128, 128, identity_map(128, 128));
+    add(L.vis2_0, 128, 128, 128, identity_map(128, 128));
+  }
+  const size_t img_bytes = (img.size() + 255) & ~(size_t)255;
+  const size_t need = img_bytes + tab.size() * sizeof(FusedChunk);
+  if (need > dst_bytes) return fail(DYN_E_INVALID, "twin images need %zu bytes, have %zu", need, dst_bytes);
+  DYN_CUDA(cudaMemcpyAsync(dst_dev, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+  DYN_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(dst_dev) + img_bytes, tab.data(),
+                           tab.size() * sizeof(FusedChunk), cudaMemcpyHostToDevice, st));
+  DYN_CUDA(cudaStreamSynchronize(st));
+  n->twin.img = dst_dev;
+  n->twin.tab = reinterpret_cast<const FusedChunk*>(reinterpret_cast<char*>(dst_dev) + img_bytes);
+  n->twin.nchunks = (int)tab.size();
+  return DYN_OK;
+}
+
+int launch_view_twin(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st) {
+  if (n->twin.img == nullptr) return fail(DYN_E_INVALID, "net has no twin-warp view images");
+  a.wimg = n->twin.img;
+  a.chunks = n->twin.tab;
+  a.nchunks = n->twin.nchunks;
+  int dev = 0, sms = 148;
+  DYN_CUDA(cudaGetDevice(&dev));
+  DYN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int VP = V <= 8 ? 8 : 16;
+  const long long n_iter = (a.P * VP + 255) / 256;
+  const int grid = (int)(n_iter < sms ? n_iter : sms);
+  if (grid == 0) return DYN_OK;
+  const bool st_net = n->kind == DYN_NET_STATIC;
+  ProfScope prof(st_net ? PROF_VIEW_ST : PROF_VIEW_DY, st);
+#define LAUNCH_VT(VPV, STV)                                                                  \
+  do {                                                                                       \
+    DYN_CUDA(cudaFuncSetAttribute(view_twin_kernel<VPV, STV>,                                \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTwin));  \
+    view_twin_kernel<VPV, STV><<<grid, 576, kSmemTwin, st>>>(a);                             \
+  } while (0)
+  if (st_net) { if (VP == 8) LAUNCH_VT(8, true); else LAUNCH_VT(16, true); }
+  else { if (VP == 8) LAUNCH_VT(8, false); else LAUNCH_VT(16, false); }
+#undef LAUNCH_VT
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
+}  // namespace dyn
