@@ -211,6 +211,7 @@ int dyn_net_static_fused(dyn_net_t net, const float* pts, const float* ray_o, co
                          const float* feat_cl, int R, int S, int V, int H, int W, int C, int h, int w,
                          float* raw, float* mask_out, void* workspace, size_t workspace_bytes,
                          void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(net && net->kind == DYN_NET_STATIC && pts && ray_o && ray_d && query_cam && src_rgbs);
   DYN_CHECK_ARG(src_cams && feat_cl && raw && mask_out && workspace && C == kC);
   DYN_CHECK_ARG(R >= 0 && S >= 1 && V >= 1 && V <= 16);
@@ -224,6 +225,7 @@ int dyn_net_dynamic_fused(dyn_net_t net, const float* pts, const float* pts_seq,
                           const float* feat_cl, float time, int R, int S, int V, int H, int W, int C,
                           int h, int w, float* raw, float* mask_out, void* workspace,
                           size_t workspace_bytes, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(net && net->kind == DYN_NET_DYNAMIC && pts && pts_seq && ray_dir && query_cam);
   DYN_CHECK_ARG(src_rgbs && src_cams && feat_cl && raw && mask_out && workspace && C == kC);
   DYN_CHECK_ARG(R >= 0 && S >= 1 && V >= 1 && V <= 16);
@@ -242,6 +244,7 @@ int dyn_debug_point_chain(dyn_net_t net, const float* G, const float* nvalid, co
 
 int dyn_motion_coeffs(dyn_net_t motion, const float* pts, float time, int R, int S, float* coeff,
                       void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(motion && motion->kind == DYN_NET_MOTION && pts && coeff && workspace);
   DYN_CHECK_ARG(R >= 0 && S >= 1);
   DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
@@ -262,6 +265,7 @@ int dyn_motion_mlp(dyn_net_t motion, const float* xyzt, int N, float* coeff, voi
 int dyn_net_dynamic(dyn_net_t net, const float* pts, const float* rgb_feat, const float* ray_dir,
                     const float* mask, float time, int R, int S, int V, float* raw, void* workspace,
                     size_t workspace_bytes, int precision, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(net && net->kind == DYN_NET_DYNAMIC && pts && rgb_feat && ray_dir && mask && raw);
   DYN_CHECK_ARG(workspace && R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
   DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
@@ -272,6 +276,7 @@ int dyn_net_dynamic(dyn_net_t net, const float* pts, const float* rgb_feat, cons
 int dyn_net_static(dyn_net_t net, const float* pts, const float* ref_rays, const float* src_rays,
                    const float* rgb_feat, const float* ray_diff, const float* mask, int R, int S, int V,
                    float* raw, void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(net && net->kind == DYN_NET_STATIC && pts && ref_rays && src_rays && rgb_feat);
   DYN_CHECK_ARG(ray_diff && mask && raw && workspace && R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
   DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);

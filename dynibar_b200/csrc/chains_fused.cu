@@ -503,16 +503,13 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
       const long long m = pl * a.V + v;
       // operand: [x (128) | vis2, ray_diff (4) | 0 ...] = 144 columns
       {
-        const float4* src = reinterpret_cast<const float4*>(a.X + m * 128);
+        // x was spilled as bf16 by the per-view kernel: 16-byte chunks go straight into the tile
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.X) + m * 128);
 #pragma unroll 4
         for (int g = 0; g < 16; ++g) {
-          float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (valid) {
-            const float4 q0 = __ldg(src + 2 * g), q1 = __ldg(src + 2 * g + 1);
-            t[0] = q0.x; t[1] = q0.y; t[2] = q0.z; t[3] = q0.w;
-            t[4] = q1.x; t[5] = q1.y; t[6] = q1.z; t[7] = q1.w;
-          }
-          store8(arow, 8 * g, t);
+          uint4 q = make_uint4(0u, 0u, 0u, 0u);
+          if (valid) q = __ldg(src + g);
+          *reinterpret_cast<uint4*>(arow + g * 2048) = q;
         }
         float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (valid) {

@@ -207,6 +207,7 @@ extern "C" {
 int dyn_composite(const float* raw_dy, const float* raw_st, const float* z_vals, const float* mask_dy,
                   int V_dy, int min_views_dy, const float* mask_st, int V_st, int min_views_st, int R,
                   int S, float* out_rays, float* out_samples, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(raw_dy && raw_st && z_vals && mask_dy && mask_st && out_rays && out_samples);
   DYN_CHECK_ARG(R >= 0 && S >= 1 && V_dy >= 1 && V_st >= 1);
   if (R == 0) return DYN_OK;
@@ -220,6 +221,7 @@ int dyn_composite(const float* raw_dy, const float* raw_st, const float* z_vals,
 int dyn_composite_vanilla(const float* raw, const float* z_vals, const float* mask, int V,
                           int min_views, int R, int S, float* out_rays, float* out_samples,
                           void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(raw && z_vals && mask && out_rays && out_samples && R >= 0 && S >= 1 && V >= 1);
   if (R == 0) return DYN_OK;
   composite_kernel<false><<<cdiv((long long)R * 32, 128), 128, 0, (cudaStream_t)stream>>>(
@@ -230,6 +232,7 @@ int dyn_composite_vanilla(const float* raw, const float* z_vals, const float* ma
 
 int dyn_resample(const float* z_vals, const float* weights, const float* u, int R, int S, int Ni,
                  int inv_uniform, float* z_out, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(z_vals && weights && z_out && R >= 0 && S >= 3 && Ni >= 2);
   DYN_CHECK_ARG(S + Ni <= 1024);
   if (R == 0) return DYN_OK;

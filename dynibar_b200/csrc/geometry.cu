@@ -128,9 +128,13 @@ __global__ void to_channels_last_kernel(const float* __restrict__ in, float* __r
   }
 }
 
-// 8 lanes cooperate on one (point, view) pair: lane j gathers feature
-// channels 4j..4j+3 (float4 taps from the channels-last map); lanes 0..2 also
-// gather one RGB channel each; lane 0 writes mask and ray_diff.
+// Stand-alone projection + gather (Projector.compute_with_motions).
+// A 256-thread block owns 32 consecutive (point, view) pairs = 32 x 35 floats of
+// contiguous rgb_feat output.  8 lanes cooperate on one pair: lane 0 of the octet
+// does the projection / masks / view-angle math once and broadcasts the sampling
+// position with shuffles; lane j gathers feature channels 4j..4j+3 (float4 taps
+// from the channels-last map) and lanes 0..2 one RGB channel each.  Results are
+// staged in shared memory and written with coalesced 16-byte stores.
 // Bilinear, zero padding, align_corners=True, coordinates normalised by the
 // SOURCE IMAGE size for both maps (projection.py:22-30, :143-158).
 __global__ void __launch_bounds__(256)
@@ -139,72 +143,34 @@ project_gather_kernel(const float* __restrict__ xyz_st, const float* __restrict_
                       const __grid_constant__ ViewCams cams, int V, long long N /* R*S */, int H,
                       int W, int h, int w, float* __restrict__ rgb_feat,
                       float* __restrict__ ray_diff, float* __restrict__ mask) {
-  long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  int lane8 = threadIdx.x & 7;
-  if (gid >= N * V) return;
-  long long pt = gid / V;
-  int v = (int)(gid % V);
-  float sx = xyz_st[pt * 3], sy = xyz_st[pt * 3 + 1], sz = xyz_st[pt * 3 + 2];
-  float x = sx, y = sy, z = sz;
-  if (xyz != nullptr) {
-    const float* q = xyz + ((long long)v * N + pt) * 3;
-    x = q[0]; y = q[1]; z = q[2];
-  }
-  float u, vv;
-  bool front;
-  project_point(cams.P[v], x, y, z, u, vv, front);
-  // normalise with the image size, un-normalise with each map's own size
-  float gx = 2.f * u / (cams.w_img - 1.f) - 1.f;
-  float gy = 2.f * vv / (cams.h_img - 1.f) - 1.f;
-
-  float* out = rgb_feat + gid * kF;
-  {  // deep features, channels 4*lane8 .. +3
-    float fx = (gx + 1.f) * 0.5f * (float)(w - 1);
-    float fy = (gy + 1.f) * 0.5f * (float)(h - 1);
-    float x0f = floorf(fx), y0f = floorf(fy);
-    int x0 = (int)x0f, y0 = (int)y0f;
-    float ax = fx - x0f, ay = fy - y0f;              // ATen grid_sampler weights:
-    float bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;  // (ix_se - ix) etc.
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* base = feat_cl + (long long)v * h * w * kC + lane8 * 4;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        int xi = x0 + dx, yi = y0 + dy;
-        float wgt = (dx ? ax : bx) * (dy ? ay : by);
-        if (xi >= 0 && xi < w && yi >= 0 && yi < h) {
-          float4 t = __ldg(reinterpret_cast<const float4*>(base + ((long long)yi * w + xi) * kC));
-          acc.x += t.x * wgt; acc.y += t.y * wgt; acc.z += t.z * wgt; acc.w += t.w * wgt;
-        }
-      }
-    out[3 + lane8 * 4 + 0] = acc.x;
-    out[3 + lane8 * 4 + 1] = acc.y;
-    out[3 + lane8 * 4 + 2] = acc.z;
-    out[3 + lane8 * 4 + 3] = acc.w;
-  }
-  if (lane8 < 3) {  // RGB channel lane8 from [V,H,W,3]
-    float fx = (gx + 1.f) * 0.5f * (float)(W - 1);
-    float fy = (gy + 1.f) * 0.5f * (float)(H - 1);
-    float x0f = floorf(fx), y0f = floorf(fy);
-    int x0 = (int)x0f, y0 = (int)y0f;
-    float ax = fx - x0f, ay = fy - y0f;              // ATen grid_sampler weights:
-    float bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;  // (ix_se - ix) etc.
-    float acc = 0.f;
-    const float* base = rgbs + (long long)v * H * W * 3 + lane8;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        int xi = x0 + dx, yi = y0 + dy;
-        float wgt = (dx ? ax : bx) * (dy ? ay : by);
-        if (xi >= 0 && xi < W && yi >= 0 && yi < H)
-          acc += __ldg(base + ((long long)yi * W + xi) * 3) * wgt;
-      }
-    out[lane8] = acc;
-  }
-  if (lane8 == 0) {
-    bool inb = (u <= cams.w_img - 1.f) && (u >= 0.f) && (vv <= cams.h_img - 1.f) && (vv >= 0.f);
+  __shared__ __align__(16) float stage[32 * kF];
+  const long long pair0 = (long long)blockIdx.x * 32;
+  const int lp = threadIdx.x >> 3;        // local pair
+  const int lane8 = threadIdx.x & 7;
+  const long long gid = pair0 + lp;
+  const long long total = N * V;
+  const bool ok = gid < total;
+  float gx = 0.f, gy = 0.f;
+  int v = 0;
+  // (point, view) of this pair without a per-thread 64-bit division: one uniform
+  // division per block, then small 32-bit arithmetic
+  const long long q0 = pair0 / V;
+  const int t0 = (int)(pair0 - q0 * V) + lp;
+  if (lane8 == 0 && ok) {
+    const long long pt = q0 + t0 / V;
+    v = t0 % V;
+    const float sx = xyz_st[pt * 3], sy = xyz_st[pt * 3 + 1], sz = xyz_st[pt * 3 + 2];
+    float x = sx, y = sy, z = sz;
+    if (xyz != nullptr) {
+      const float* q = xyz + ((long long)v * N + pt) * 3;
+      x = q[0]; y = q[1]; z = q[2];
+    }
+    float u, vv;
+    bool front;
+    project_point(cams.P[v], x, y, z, u, vv, front);
+    gx = 2.f * u / (cams.w_img - 1.f) - 1.f;
+    gy = 2.f * vv / (cams.h_img - 1.f) - 1.f;
+    const bool inb = (u <= cams.w_img - 1.f) && (u >= 0.f) && (vv <= cams.h_img - 1.f) && (vv >= 0.f);
     mask[gid] = (inb && front) ? 1.f : 0.f;
     // compute_angle, projection.py:61-101
     float a0 = cams.tgt[0] - sx, a1 = cams.tgt[1] - sy, a2 = cams.tgt[2] - sz;
@@ -212,9 +178,70 @@ project_gather_kernel(const float* __restrict__ xyz_st, const float* __restrict_
     float b0 = cams.center[v][0] - x, b1 = cams.center[v][1] - y, b2 = cams.center[v][2] - z;
     normalize3(b0, b1, b2);
     float d0 = a0 - b0, d1 = a1 - b1, d2 = a2 - b2;
-    float dot = a0 * b0 + a1 * b1 + a2 * b2;
+    const float dot = a0 * b0 + a1 * b1 + a2 * b2;
     normalize3(d0, d1, d2);
     reinterpret_cast<float4*>(ray_diff)[gid] = make_float4(d0, d1, d2, dot);
+  }
+  // broadcast the sampling position inside the octet
+  const unsigned src = (threadIdx.x & 31) & ~7u;
+  gx = __shfl_sync(0xffffffffu, gx, src);
+  gy = __shfl_sync(0xffffffffu, gy, src);
+  v = __shfl_sync(0xffffffffu, v, src);
+  if (ok) {
+    {  // deep features, channels 4*lane8 .. +3
+      const float fx = (gx + 1.f) * 0.5f * (float)(w - 1);
+      const float fy = (gy + 1.f) * 0.5f * (float)(h - 1);
+      const float x0f = floorf(fx), y0f = floorf(fy);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const float ax = fx - x0f, ay = fy - y0f;              // ATen grid_sampler weights:
+      const float bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;  // (ix_se - ix) etc.
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* base = feat_cl + (size_t)v * (size_t)(h * w * kC) + lane8 * 4;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int xi = x0 + dx, yi = y0 + dy;
+          const float wgt = (dx ? ax : bx) * (dy ? ay : by);
+          if (xi >= 0 && xi < w && yi >= 0 && yi < h) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(base + (yi * w + xi) * kC));
+            acc.x += t.x * wgt; acc.y += t.y * wgt; acc.z += t.z * wgt; acc.w += t.w * wgt;
+          }
+        }
+      float* o = stage + lp * kF + 3 + lane8 * 4;
+      o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+    }
+    if (lane8 < 3) {  // RGB channel lane8 from [V,H,W,3]
+      const float fx = (gx + 1.f) * 0.5f * (float)(W - 1);
+      const float fy = (gy + 1.f) * 0.5f * (float)(H - 1);
+      const float x0f = floorf(fx), y0f = floorf(fy);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const float ax = fx - x0f, ay = fy - y0f;
+      const float bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
+      float acc = 0.f;
+      const float* base = rgbs + (size_t)v * (size_t)(H * W * 3) + lane8;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int xi = x0 + dx, yi = y0 + dy;
+          const float wgt = (dx ? ax : bx) * (dy ? ay : by);
+          if (xi >= 0 && xi < W && yi >= 0 && yi < H)
+            acc += __ldg(base + (yi * W + xi) * 3) * wgt;
+        }
+      stage[lp * kF + lane8] = acc;
+    }
+  }
+  __syncthreads();
+  // 32 pairs x 35 floats = 1120 contiguous floats (pair0 * 35 floats is 16-byte aligned: 32*35*4 B per block)
+  const long long n_out = (total - pair0 < 32 ? total - pair0 : 32) * kF;
+  float* dst = rgb_feat + pair0 * kF;
+  for (int i = threadIdx.x * 4; i < n_out; i += 256 * 4) {
+    if (i + 4 <= n_out) {
+      *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(stage + i);
+    } else {
+      for (int j = i; j < n_out; ++j) dst[j] = stage[j];
+    }
   }
 }
 
@@ -455,6 +482,7 @@ extern "C" {
 int dyn_sample_rays(const float* ray_o, const float* ray_d, float near_depth, float far_depth, int R,
                     int S, int inv_uniform, const float* jitter, float* pts, float* z_vals,
                     float* s_vals, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(ray_o && ray_d && pts && z_vals && R >= 0 && S >= 2);
   DYN_CHECK_ARG(near_depth > 0 && far_depth > near_depth);  // render_ray.py:90-94
   if (R == 0) return DYN_OK;
@@ -468,6 +496,7 @@ int dyn_sample_rays(const float* ray_o, const float* ray_d, float near_depth, fl
 int dyn_points_from_depths(const float* ray_o, const float* ray_d, const float* z_vals,
                            float near_depth, float far_depth, int R, int S, float* pts,
                            float* s_vals, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(ray_o && ray_d && z_vals && pts && R >= 0 && S >= 1);
   if (R == 0) return DYN_OK;
   long long n = (long long)R * S;
@@ -480,6 +509,7 @@ int dyn_points_from_depths(const float* ray_o, const float* ray_d, const float* 
 int dyn_traj_displace(const float* pts, const float* coeff, const float* basis, int T, int nb,
                       int frame_idx, const int* offsets_host, int n_off, int num_vv, int R, int S,
                       float* pts_seq, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(pts && coeff && basis && pts_seq && (offsets_host || n_off == 0));
   DYN_CHECK_ARG(nb >= 1 && nb <= 8 && n_off >= 0 && num_vv >= 0 && n_off + num_vv <= kMaxViews);
   if (R == 0) return DYN_OK;
@@ -512,6 +542,7 @@ int dyn_project_gather(const float* xyz_st, const float* xyz, const float* query
                        const float* src_rgbs, const float* src_cams, const float* featmaps, int V,
                        int R, int S, int H, int W, int C, int h, int w, float* feat_cl_ws,
                        float* rgb_feat, float* ray_diff, float* mask, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(xyz_st && query_cam && src_rgbs && src_cams && featmaps && feat_cl_ws);
   DYN_CHECK_ARG(rgb_feat && ray_diff && mask);
   DYN_CHECK_ARG(C == kC && V >= 1 && V <= kMaxViews && H > 1 && W > 1 && h > 1 && w > 1);
@@ -524,9 +555,8 @@ int dyn_project_gather(const float* xyz_st, const float* xyz, const float* query
   to_channels_last_kernel<<<tg, tb, 0, st>>>(featmaps, feat_cl_ws, C, h * w);
   DYN_LAUNCH_CHECK();
   long long N = (long long)R * S;
-  long long threads = N * V * 8;
   ProfScope prof(PROF_GATHER, st);
-  project_gather_kernel<<<cdiv(threads, 256), 256, 0, st>>>(xyz_st, xyz, src_rgbs, feat_cl_ws, vc,
+  project_gather_kernel<<<cdiv(N * V, 32), 256, 0, st>>>(xyz_st, xyz, src_rgbs, feat_cl_ws, vc,
                                                             V, N, H, W, h, w, rgb_feat, ray_diff,
                                                             mask);
   DYN_LAUNCH_CHECK();
@@ -547,6 +577,7 @@ int dyn_compute_projections(const float* xyz, const float* src_cams, int V, int 
 }
 
 int dyn_plucker_ref(const float* ray_o, const float* ray_d, int R, float* out6, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(ray_o && ray_d && out6 && R >= 0);
   if (R == 0) return DYN_OK;
   plucker_ref_kernel<<<cdiv(R, 256), 256, 0, (cudaStream_t)stream>>>(ray_o, ray_d, R, out6);
@@ -556,6 +587,7 @@ int dyn_plucker_ref(const float* ray_o, const float* ray_d, int R, float* out6, 
 
 int dyn_plucker_src(const float* pts, const float* src_cams, int V, int R, int S, float* out,
                     void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(pts && src_cams && out && R >= 0);
   if (R == 0) return DYN_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -572,6 +604,7 @@ int dyn_flow_sceneflow(const float* weights, const float* pts_seq, const float* 
                        const float* uv, const float* coeff, const float* basis, int T, int nb,
                        int frame_idx, int sf_k, int n_flow, int R, int S, float* flows,
                        float* exp_sf, void* stream) {
+  if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(weights && pts_seq && src_cams && uv && flows);
   DYN_CHECK_ARG(n_flow >= 0 && n_flow <= kMaxViews && nb >= 1 && nb <= 8);
   if (R == 0) return DYN_OK;

@@ -380,9 +380,12 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
         for (int i = 0; i < 32; ++i) xs[i] += elu_fast(acc[i] + cst[C_B6 + cb * 32 + i]);
         tmem_st32(tacc + 128 + cb * 32, xs);
         if (ST && valid) {
-          float4* xo = reinterpret_cast<float4*>(a.X + m * 128 + cb * 32);
+          // spilled as bf16: its only consumer is the blending head's A operand
+          uint4* xo = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.X) + m * 128 + cb * 32);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xo[i] = make_float4(xs[4 * i], xs[4 * i + 1], xs[4 * i + 2], xs[4 * i + 3]);
+          for (int i = 0; i < 4; ++i)
+            xo[i] = make_uint4(pack_bf16x2(xs[8 * i], xs[8 * i + 1]), pack_bf16x2(xs[8 * i + 2], xs[8 * i + 3]),
+                               pack_bf16x2(xs[8 * i + 4], xs[8 * i + 5]), pack_bf16x2(xs[8 * i + 6], xs[8 * i + 7]));
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) xs[i] *= vis1;

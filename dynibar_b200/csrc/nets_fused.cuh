@@ -41,7 +41,7 @@ struct ViewFusedArgs {
   float* nvalid;     // [P]
   float* mask_proj;  // [P*V] projector mask (in front & in bounds)
   float* mask_eff;   // static [P*V]: mask after mask_rgb gating
-  float* X;          // static [P*V,128]: per-view feature after the visibility residual
+  float* X;          // static [P*V,128] **bf16** (declared float* for the workspace): per-view feature after the visibility residual
   float* vis2;       // static [P*V]
   float* ray_diff;   // static [P*V,4]
   float* rgb_in;     // static [P*V,3] gathered source colours
@@ -97,7 +97,7 @@ struct Point2Args {
 };
 
 struct RgbHeadArgs {
-  const float *X, *vis2, *ray_diff, *mask_eff, *rgb_in, *GW, *sigma;
+  const float *X /* bf16 [P*V,128] */, *vis2, *ray_diff, *mask_eff, *rgb_in, *GW, *sigma;
   long long P;
   int V;
   float* raw;  // [P,4]

@@ -407,9 +407,12 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
         for (int i = 0; i < 32; ++i) xs[i] += elu_fast(acc[i] + cst[T_B6 + cb + i]);
         tmem_st32(tacc + 128 + cb, xs);
         if (ST && valid) {
-          float4* xo = reinterpret_cast<float4*>(a.X + m * 128 + cb);
+          // spilled as bf16: its only consumer is the blending head's A operand
+          uint4* xo = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.X) + m * 128 + cb);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xo[i] = make_float4(xs[4 * i], xs[4 * i + 1], xs[4 * i + 2], xs[4 * i + 3]);
+          for (int i = 0; i < 4; ++i)
+            xo[i] = make_uint4(pack_bf16x2(xs[8 * i], xs[8 * i + 1]), pack_bf16x2(xs[8 * i + 2], xs[8 * i + 3]),
+                               pack_bf16x2(xs[8 * i + 4], xs[8 * i + 5]), pack_bf16x2(xs[8 * i + 6], xs[8 * i + 7]));
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) xs[i] *= vis1;
