@@ -31,9 +31,9 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32_bmn(int M, int N) {
 // Warp-cooperative load of this warp's 32 rows of a [*,128] fp32 matrix into the
 // canonical bf16 tile.  Per instruction pair a warp covers 8 rows x 32 columns:
 // lane l -> row (l % 8), k-group (l / 8): 128 contiguous bytes per row in global
-// memory, and the 8 lanes of every quarter-warp hit 8 different 16-byte rows of one
+// memory (rows are already bf16), and the 8 lanes of every quarter-warp hit 8 different 16-byte rows of one
 // core matrix in shared memory (conflict-free STS.128).
-__device__ __forceinline__ void warp_rows_to_tile(uint8_t* tile, const float* __restrict__ src,
+__device__ __forceinline__ void warp_rows_to_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ src,
                                                   long long row0, long long P, int warp, int lane) {
 #pragma unroll
   for (int rg = 0; rg < 4; ++rg) {
@@ -43,20 +43,16 @@ __device__ __forceinline__ void warp_rows_to_tile(uint8_t* tile, const float* __
     for (int kq = 0; kq < 4; ++kq) {
       const int kg = kq * 4 + (lane >> 3);
       uint4 q = make_uint4(0u, 0u, 0u, 0u);
-      if (row < P) {
-        const float4* s4 = reinterpret_cast<const float4*>(src + row * 128 + kg * 8);
-        const float4 a = __ldg(s4), b = __ldg(s4 + 1);
-        q.x = pack_bf16x2(a.x, a.y); q.y = pack_bf16x2(a.z, a.w);
-        q.z = pack_bf16x2(b.x, b.y); q.w = pack_bf16x2(b.z, b.w);
-      }
+      if (row < P) q = __ldg(reinterpret_cast<const uint4*>(src + row * 128 + kg * 8));
       *reinterpret_cast<uint4*>(tile + kg * 2048 + (r >> 3) * 128 + (r & 7) * 16) = q;
     }
   }
 }
 
 __global__ void __launch_bounds__(128, 2)
-attention_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
-                    const float* __restrict__ nvalid, long long P, int S, float* __restrict__ O) {
+attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K,
+                    const __nv_bfloat16* __restrict__ V, const float* __restrict__ nvalid, long long P, int S,
+                    __nv_bfloat16* __restrict__ O) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* kt = smem;
   uint8_t* vt = smem + kTile;
@@ -97,12 +93,7 @@ attention_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         qreg[g] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok) {
-          const float4* s4 = reinterpret_cast<const float4*>(Q + row * 128 + h * 32 + g * 8);
-          const float4 a = __ldg(s4), b = __ldg(s4 + 1);
-          qreg[g].x = pack_bf16x2(a.x, a.y); qreg[g].y = pack_bf16x2(a.z, a.w);
-          qreg[g].z = pack_bf16x2(b.x, b.y); qreg[g].w = pack_bf16x2(b.z, b.w);
-        }
+        if (ok) qreg[g] = __ldg(reinterpret_cast<const uint4*>(Q + row * 128 + h * 32 + g * 8));
       }
     };
     load_q(0);
@@ -202,10 +193,13 @@ attention_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
       tmem_wait_ld();
       if (ok) {
         const float inv = invs[h];
-        float4* dst = reinterpret_cast<float4*>(O + row * 128 + 32 * h);
+        uint4* dst = reinterpret_cast<uint4*>(O + row * 128 + 32 * h);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+        for (int i = 0; i < 4; ++i)
+          dst[i] = make_uint4(pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv),
+                              pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
+                              pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv),
+                              pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
       }
     }
     tc_fence_before_sync();
@@ -221,8 +215,8 @@ attention_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
 
 bool attention_tc_supported(int S) { return S >= 1 && S <= 128 && (128 % S) == 0; }
 
-int launch_attention_tc(const float* Q, const float* K, const float* V, const float* nvalid, long long P,
-                        int S, float* O, cudaStream_t st) {
+int launch_attention_tc(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V,
+                        const float* nvalid, long long P, int S, __nv_bfloat16* O, cudaStream_t st) {
   if (P == 0) return DYN_OK;
   int dev = 0, sms = 148;
   DYN_CUDA(cudaGetDevice(&dev));

@@ -246,17 +246,19 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
         }
       }
       operand_ready(bar0, bt);
-      wait_acc(bar0, bt, acc_cnt);  // [Wq ; Wk] (N = 256, no bias)
+      wait_acc(bar0, bt, acc_cnt);  // [Wq ; Wk] (N = 256, no bias) -> bf16 rows (operands of the attention)
 #pragma unroll 1
       for (int cb = 0; cb < 256; cb += 32) {
         float acc[32];
         tmem_ld32(tacc + cb, acc);
         tmem_wait_ld();
         if (valid) {
-          float* base = (cb < 128 ? a.Q : a.K) + row * 128 + (cb & 127);
-          float4* o = reinterpret_cast<float4*>(base);
+          __nv_bfloat16* base = (cb < 128 ? a.Q : a.K) + row * 128 + (cb & 127);
+          uint4* o = reinterpret_cast<uint4*>(base);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+          for (int i = 0; i < 4; ++i)
+            o[i] = make_uint4(pack_bf16x2(acc[8 * i], acc[8 * i + 1]), pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]),
+                              pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]), pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7]));
         }
       }
       tc_fence_before_sync();
@@ -268,9 +270,11 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
         tmem_ld32(tacc + cb, acc);
         tmem_wait_ld();
         if (valid) {
-          float4* o = reinterpret_cast<float4*>(a.V + row * 128 + cb);
+          uint4* o = reinterpret_cast<uint4*>(a.V + row * 128 + cb);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+          for (int i = 0; i < 4; ++i)
+            o[i] = make_uint4(pack_bf16x2(acc[8 * i], acc[8 * i + 1]), pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]),
+                              pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]), pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7]));
         }
       }
       tc_fence_before_sync();
@@ -327,18 +331,14 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
     for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
       const long long row = (long long)it * 256 + tid;
       const bool valid = row < a.P;
-      // operand: attention output O (128)
+      // operand: attention output O (128 bf16): 16-byte chunks go straight into the tile
       {
-        const float4* src = reinterpret_cast<const float4*>(a.O + row * 128);
+        const uint4* src = reinterpret_cast<const uint4*>(a.O + row * 128);
 #pragma unroll 4
         for (int g = 0; g < 16; ++g) {
-          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (valid) {
-            const float4 q0 = __ldg(src + 2 * g), q1 = __ldg(src + 2 * g + 1);
-            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
-            v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-          }
-          store8(arow, 8 * g, v);
+          uint4 q = make_uint4(0u, 0u, 0u, 0u);
+          if (valid) q = __ldg(src + g);
+          *reinterpret_cast<uint4*>(arow + g * 2048) = q;
         }
       }
       operand_ready(bar0, bt);

@@ -1,5 +1,7 @@
 // Internal interfaces between the network implementations and the C ABI.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dyn {
@@ -33,8 +35,8 @@ int debug_point_chain(const dyn_net* n, const float* G, const float* nvalid, con
                       float* O, float* out_a, float* out_b, float* posenc_ws, cudaStream_t st);
 // tcgen05 ray-transformer attention (attention_tc.cu); S must divide 128
 bool attention_tc_supported(int S);
-int launch_attention_tc(const float* Q, const float* K, const float* V, const float* nvalid, long long P,
-                        int S, float* O, cudaStream_t st);
+int launch_attention_tc(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V,
+                        const float* nvalid, long long P, int S, __nv_bfloat16* O, cudaStream_t st);
 int zero_last_samples(float* coeff, int R, int S, int width, cudaStream_t st);
 
 }  // namespace dyn

@@ -325,9 +325,34 @@ __global__ void posenc_table_kernel(float* __restrict__ tab, int S) {
 // Masked QUERY rows get all logits = -1e9 -> uniform attention
 // (mlp_network.py:23-24, :91-94).
 // ---------------------------------------------------------------------------
-__global__ void attention_kernel(const float* __restrict__ Q, const float* __restrict__ K,
-                                 const float* __restrict__ Vv, const float* __restrict__ nvalid, int S,
-                                 float* __restrict__ O) {
+// 4 consecutive elements of a [*,128] row stored as fp32 or bf16
+template <bool BF>
+__device__ __forceinline__ float4 ld4(const void* base, long long elem) {
+  if (BF) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
+}
+template <bool BF>
+__device__ __forceinline__ void st4(void* base, long long elem, float4 v) {
+  if (BF) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + elem) = u;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem) = v;
+  }
+}
+
+// BF: Q/K/V/O are bf16 rows (fused path) instead of fp32 (staged path)
+template <bool BF>
+__global__ void attention_kernel(const void* __restrict__ Q, const void* __restrict__ K,
+                                 const void* __restrict__ Vv, const float* __restrict__ nvalid, int S,
+                                 void* __restrict__ O) {
   extern __shared__ __align__(16) float sm[];
   float4* Ks = reinterpret_cast<float4*>(sm);          // [S][8] float4 = 32 floats per key
   float4* Vs = reinterpret_cast<float4*>(sm) + S * 8;  // [S][8]
@@ -340,15 +365,15 @@ __global__ void attention_kernel(const float* __restrict__ Q, const float* __res
     __syncthreads();
     for (int e = threadIdx.x; e < S * 8; e += blockDim.x) {
       int j = e >> 3, d4 = e & 7;
-      Ks[e] = *reinterpret_cast<const float4*>(K + (base + j) * 128 + h * 32 + d4 * 4);
-      Vs[e] = *reinterpret_cast<const float4*>(Vv + (base + j) * 128 + h * 32 + d4 * 4);
+      Ks[e] = ld4<BF>(K, (base + j) * 128 + h * 32 + d4 * 4);
+      Vs[e] = ld4<BF>(Vv, (base + j) * 128 + h * 32 + d4 * 4);
     }
     __syncthreads();
     if (i < S) {
       float q[32], o[32];
 #pragma unroll
       for (int d4 = 0; d4 < 8; ++d4) {
-        float4 t = *reinterpret_cast<const float4*>(Q + (base + i) * 128 + h * 32 + d4 * 4);
+        float4 t = ld4<BF>(Q, (base + i) * 128 + h * 32 + d4 * 4);
         q[4 * d4] = t.x * inv_temp; q[4 * d4 + 1] = t.y * inv_temp;
         q[4 * d4 + 2] = t.z * inv_temp; q[4 * d4 + 3] = t.w * inv_temp;
       }
@@ -384,8 +409,8 @@ __global__ void attention_kernel(const float* __restrict__ Q, const float* __res
       const float inv = 1.f / den;
 #pragma unroll
       for (int d4 = 0; d4 < 8; ++d4)
-        *reinterpret_cast<float4*>(O + (base + i) * 128 + h * 32 + d4 * 4) =
-            make_float4(o[4 * d4] * inv, o[4 * d4 + 1] * inv, o[4 * d4 + 2] * inv, o[4 * d4 + 3] * inv);
+        st4<BF>(O, (base + i) * 128 + h * 32 + d4 * 4,
+                make_float4(o[4 * d4] * inv, o[4 * d4 + 1] * inv, o[4 * d4 + 2] * inv, o[4 * d4 + 3] * inv));
     }
   }
 }
@@ -578,9 +603,9 @@ static int run_point_tail(const dyn_net* n, const Layout& L, const float* G, int
     size_t smem = (size_t)2 * S * 32 * sizeof(float);
     if (threads > 1024) return fail(DYN_E_INVALID, "ray transformer supports S <= 1024 (got %d)", S);
     if (smem > 48 * 1024)
-      DYN_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      DYN_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-    attention_kernel<<<R, threads, smem, st>>>(t.Q, t.K, t.V, t.nvalid, S, t.O);
+    attention_kernel<false><<<R, threads, smem, st>>>(t.Q, t.K, t.V, t.nvalid, S, t.O);
     DYN_LAUNCH_CHECK();
   }
   RUN(run_lin(n, L.fc, L1(n, L.fc, t.O, t.O2, P, ACT_NONE), prec, st));
@@ -856,7 +881,12 @@ static int run_point_fused(const dyn_net* n, const float* G, long long P, int R,
                            float* posenc_tab, TrunkBufs& t, Point2Args& p2, cudaStream_t st) {
   Point1Args p1;
   memset(&p1, 0, sizeof(p1));
-  p1.G = G; p1.P = P; p1.S = S; p1.g2 = t.G2; p1.Q = t.Q; p1.K = t.K; p1.V = t.V;
+  // Q, K, V, O travel between the point kernels as bf16 rows (they are tensor-core operands)
+  __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(t.Q);
+  __nv_bfloat16* Kb = reinterpret_cast<__nv_bfloat16*>(t.K);
+  __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(t.V);
+  __nv_bfloat16* Ob = reinterpret_cast<__nv_bfloat16*>(t.O);
+  p1.G = G; p1.P = P; p1.S = S; p1.g2 = t.G2; p1.Q = Qb; p1.K = Kb; p1.V = Vb;
   p1.posenc = nullptr;
   if (dynamic) {
     posenc_table_kernel<<<cdiv((long long)S * 128, 256), 256, 0, st>>>(posenc_tab, S);
@@ -865,19 +895,19 @@ static int run_point_fused(const dyn_net* n, const float* G, long long P, int R,
   }
   RUN(launch_point1_fused(n, p1, st));
   if (attention_tc_supported(S)) {
-    RUN(launch_attention_tc(t.Q, t.K, t.V, t.nvalid, P, S, t.O, st));
+    RUN(launch_attention_tc(Qb, Kb, Vb, t.nvalid, P, S, Ob, st));
   } else {
     int threads = ((S + 31) / 32) * 32;
     size_t smem = (size_t)2 * S * 32 * sizeof(float);
     if (threads > 1024) return fail(DYN_E_INVALID, "ray transformer supports S <= 1024 (got %d)", S);
     if (smem > 48 * 1024)
-      DYN_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      DYN_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
     ProfScope prof(PROF_ATTENTION, st);
-    attention_kernel<<<R, threads, smem, st>>>(t.Q, t.K, t.V, t.nvalid, S, t.O);
+    attention_kernel<true><<<R, threads, smem, st>>>(Qb, Kb, Vb, t.nvalid, S, Ob);
     DYN_LAUNCH_CHECK();
   }
-  p2.O = t.O; p2.g2 = t.G2; p2.nvalid = t.nvalid; p2.P = P; p2.S = S;
+  p2.O = Ob; p2.g2 = t.G2; p2.nvalid = t.nvalid; p2.P = P; p2.S = S;
   return launch_point2_fused(n, p2, st);
 }
 

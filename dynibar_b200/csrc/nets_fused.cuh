@@ -1,5 +1,7 @@
 // Fused per-view tensor-core stage (nets_fused.cu): argument block + host API.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "geometry.cuh"
 
 namespace dyn {
@@ -68,7 +70,8 @@ struct Point1Args {
   const float* posenc;  // [S,128] sinusoid table (dynamic) or null
   long long P;
   int S;
-  float *g2, *Q, *K, *V;  // [P,128] each
+  float* g2;                 // [P,128] fp32 (residual of the ray transformer)
+  __nv_bfloat16 *Q, *K, *V;  // [P,128] bf16 (operands of the attention)
   const float* params;
   int o_bgeo0, o_bgeo2;
   const void* wimg;
@@ -77,7 +80,7 @@ struct Point1Args {
 };
 
 struct Point2Args {
-  const float* O;       // [P,128] attention output
+  const __nv_bfloat16* O;  // [P,128] bf16 attention output
   const float* g2;      // [P,128] residual
   const float* nvalid;  // [P]
   const float* pts;     // [P,3]   (dynamic)
