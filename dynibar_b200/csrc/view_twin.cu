@@ -23,6 +23,7 @@ using namespace fe;
 
 namespace {
 
+constexpr bool kTwinPP = true;  // ping-pong (measured 8% faster than lock-step, profiles/r01_kernels.md)
 constexpr int kTwinATile = 65536;  // K <= 256 in the per-view nets: 32 k-groups
 constexpr int T_B1 = 0, T_B2 = 256, T_B3 = 304, T_B4 = 560, T_B5 = 688, T_B6 = 816, T_W6V = 944,
               T_B7 = 1072, T_W8 = 1200, T_MISC = 1328, T_DFEAT = 1344, T_XCH = 1408;  // + 2 x 256 exchange
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
 
-  if (tid == 0) init_barriers(bar0, /*pp=*/true, /*arrivals=*/256);
+  if (tid == 0) init_barriers(bar0, kTwinPP, /*arrivals=*/256);
   {
     const float* prm = a.params;
     for (int i = tid; i < 256; i += blockDim.x) {
@@ -104,10 +105,10 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
   const int n_iter = (int)((n_rows + 255) / 256);
 
   if (warp == 17) {
-    if ((tid & 31) == 0) producer_loop<true>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<kTwinPP>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 16) {
     if ((tid & 31) == 0)
-      issuer_loop<true>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kTwinATile);
+      issuer_loop<kTwinPP>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kTwinATile);
   } else {
     const int tw = tid >> 8;           // twin index
     const int t = tid & 255;           // row slot inside the 256-row iteration
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
     const int v = t % VP;
     const int gl = t & (VP - 1);
     const int pair = warp & 7;
+    const int bt = kTwinPP ? tile : 0;  // barrier tile
     float* xch5 = cst + T_XCH;        // [2][256] partial visibility logits of vis_fc
     float* xch7 = cst + T_XCH + 512;  // [2][256] partial logits of vis_fc2
     uint32_t acc_cnt = 0;
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
         for (int g = 0; g < 7; ++g) store8(arow, 56 * tw + 8 * g, xin + 8 * g);
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(bar_aready(bar0, tile));
+        mbar_arrive(bar_aready(bar0, bt));
       }
 
       // ---- gather: rgb (both twins) + this twin's 16 feature channels ----
@@ -264,14 +266,14 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
 
       if (ST) {
         // ---- F1 epilogue: this twin's 128 of the 256 columns ----
-        mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+        mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
         tc_fence_after_sync();
         elu_block_to_A<128>(arow, tacc, 128 * tw, cst + T_B1);
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(bar_aready(bar0, tile));
+        mbar_arrive(bar_aready(bar0, bt));
         // ---- F2: src_feat (35 of 48 columns) * ref_feat; twin 0 keeps 0..17, twin 1 keeps 18..34 ----
-        mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+        mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
         tc_fence_after_sync();
         float s48[48];
         tmem_ld32(tacc, s48);
@@ -335,19 +337,19 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, tile));
+      mbar_arrive(bar_aready(bar0, bt));
 
       // ---- F3: ELU(base_fc.0), this twin's 128 columns ----
-      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
       tc_fence_after_sync();
       elu_block_to_A<128>(arow, tacc, 128 * tw, cst + T_B3);
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, tile));
+      mbar_arrive(bar_aready(bar0, bt));
 
       const int c0 = 64 * tw;  // this twin's columns of the 128-wide layers
       // ---- F4: x = ELU(base_fc.2) -> TMEM [128,256); A = x * w1 ----
-      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
       tc_fence_after_sync();
 #pragma unroll 1
       for (int cb = c0; cb < c0 + 64; cb += 32) {
@@ -365,10 +367,10 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, tile));
+      mbar_arrive(bar_aready(bar0, bt));
 
       // ---- F5: h = ELU(vis_fc.0) -> A; partial visibility logit ----
-      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
       tc_fence_after_sync();
       {
         float part = 0.f;
@@ -389,10 +391,10 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, tile));
+      mbar_arrive(bar_aready(bar0, bt));
 
       // ---- F6: x += ELU(vis_fc.2[:128]); A = x * vis1 ----
-      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
       tc_fence_after_sync();
       // both twins arrived on a_ready before this MMA ran: the partial logits are visible
       const float vlogit = cst[T_MISC + 0] + xch5[t] + xch5[256 + t];
@@ -422,10 +424,10 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, tile));
+      mbar_arrive(bar_aready(bar0, bt));
 
       // ---- F7: vis2 = sigmoid(vis_fc2.2 . ELU(vis_fc2.0)) * mask ----
-      mbar_wait(bar_acc(bar0, tile), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
       tc_fence_after_sync();
       {
         float part = 0.f;
