@@ -105,6 +105,42 @@ __global__ void traj_displace_kernel(const float* __restrict__ pts, const float*
     for (int ax = 0; ax < 3; ++ax) pts_seq[((long long)v * N + idx) * 3 + ax] = p[ax];
 }
 
+// scene-flow deltas traj(frame_a) - traj(frame_b) (render_ray.py:1101-1105)
+struct DeltaArgs {
+  float ba[8][8], bb[8][8];
+  int n, nb;
+};
+__global__ void traj_delta_kernel(const float* __restrict__ coeff, DeltaArgs a, long long N,
+                                  float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N) return;
+  const int nb = a.nb;
+  float c[24];
+  for (int j = 0; j < 3 * nb; ++j) c[j] = coeff[idx * 3 * nb + j];
+  for (int v = 0; v < a.n; ++v)
+    for (int ax = 0; ax < 3; ++ax) {
+      float sa = 0.f, sb = 0.f;
+      for (int k = 0; k < nb; ++k) { sa += c[ax * nb + k] * a.ba[v][k]; sb += c[ax * nb + k] * a.bb[v][k]; }
+      out[((long long)v * N + idx) * 3 + ax] = sa - sb;
+    }
+}
+
+// occlusion weights of the cross-time branch (render_ray.py:1224-1257); warp per ray
+__global__ void occlusion_kernel(const float* __restrict__ w_ref, const float* __restrict__ w_anc, int R,
+                                 int S, float* __restrict__ occ, float* __restrict__ occ_map) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float acc = 0.f;
+  for (int s = lane; s < S; s += 32) {
+    const float d = w_ref[(long long)r * S + s] - w_anc[(long long)r * S + s];
+    occ[(long long)r * S + s] = 1.f - fabsf(d);
+    acc += d;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) occ_map[r] = 1.f - fabsf(acc);
+}
+
 // ---------------------------------------------------------------------------
 // a4-a6 projection + gather
 // ---------------------------------------------------------------------------
@@ -534,6 +570,36 @@ int dyn_traj_displace(const float* pts, const float* coeff, const float* basis, 
   for (int k = 0; k < nb; ++k) a.b_ref[k] = hb[8 * n_off + k];
   long long N = (long long)R * S;
   traj_displace_kernel<<<cdiv(N, 256), 256, 0, st>>>(pts, coeff, a, N, pts_seq);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
+int dyn_traj_delta(const float* coeff, const float* basis, int T, int nb, const int* frames_a_host,
+                   const int* frames_b_host, int n, int R, int S, float* out, void* stream) {
+  if (R == 0) return DYN_OK;
+  DYN_CHECK_ARG(coeff && basis && frames_a_host && frames_b_host && out);
+  DYN_CHECK_ARG(n >= 1 && n <= 8 && nb >= 1 && nb <= 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  static thread_local DeltaArgs a;
+  a.n = n; a.nb = nb;
+  for (int v = 0; v < n; ++v) {
+    DYN_CHECK_ARG(frames_a_host[v] >= 0 && frames_a_host[v] < T && frames_b_host[v] >= 0 && frames_b_host[v] < T);
+    int rc = fetch_small(basis + (size_t)frames_a_host[v] * nb, nb, a.ba[v], st);
+    if (!rc) rc = fetch_small(basis + (size_t)frames_b_host[v] * nb, nb, a.bb[v], st);
+    if (rc) return rc;
+  }
+  long long N = (long long)R * S;
+  traj_delta_kernel<<<cdiv(N, 256), 256, 0, st>>>(coeff, a, N, out);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
+int dyn_occlusion_weights(const float* w_ref, const float* w_anchor, int R, int S, float* occ,
+                          float* occ_map, void* stream) {
+  if (R == 0) return DYN_OK;
+  DYN_CHECK_ARG(w_ref && w_anchor && occ && occ_map && S >= 1);
+  occlusion_kernel<<<cdiv((long long)R * 32, 256), 256, 0, (cudaStream_t)stream>>>(w_ref, w_anchor, R, S,
+                                                                                  occ, occ_map);
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }

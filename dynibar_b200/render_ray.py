@@ -144,6 +144,34 @@ def displaced_points(pts, coeff, basis, frame_idx, offsets, num_vv=0):
   return seq
 
 
+def traj_deltas(coeff, basis, frames_a, frames_b):
+  """traj(frames_a[v]) - traj(frames_b[v]) -> [n,R,S,3] (scene-flow sequence,
+  render_ray.py:1101-1105)."""
+  dev = dev_of(coeff)
+  R, S = coeff.shape[:2]
+  n = len(frames_a)
+  T, nb = basis.shape
+  out = torch.empty(n, R, S, 3, device=dev)
+  fa = (C.c_int * n)(*[int(f) for f in frames_a])
+  fb = (C.c_int * n)(*[int(f) for f in frames_b])
+  A = Args()
+  with torch.cuda.device(dev):
+    check(lib.dyn_traj_delta(A(coeff), A.host(basis), T, nb, fa, fb, n, R, S, ptr(out), stream()))
+  return out
+
+
+def occlusion_weights(w_ref, w_anchor):
+  """occ_weights, occ_weight_map (render_ray.py:1224-1257)."""
+  dev = dev_of(w_ref)
+  R, S = w_ref.shape
+  occ = torch.empty(R, S, device=dev)
+  occ_map = torch.empty(R, device=dev)
+  A = Args()
+  with torch.cuda.device(dev):
+    check(lib.dyn_occlusion_weights(A(w_ref), A(w_anchor), R, S, ptr(occ), ptr(occ_map), stream()))
+  return occ, occ_map
+
+
 # ---------------------------------------------------------------------------
 # a7
 # ---------------------------------------------------------------------------
@@ -379,7 +407,8 @@ def _with_host_copies(ray_batch, model, basis_names):
 
 
 def _render_pass(ray_batch, feat_dy, feat_st, pts, z, s, t, frame_idx, offsets, num_vv, net_dy,
-                 net_st, motion, basis, flow_views, sf_k, want_extras=True, want_vanilla_st=False):
+                 net_st, motion, basis, flow_views, sf_k, want_extras=True, want_vanilla_st=False,
+                 want_aux=False):
   """One coarse-or-fine evaluation at the reference time
   (render_ray.py:455-597 == :672-782 == :951-1096)."""
   cam, ray_o, ray_d = ray_batch["camera"], ray_batch["ray_o"], ray_batch["ray_d"]
@@ -418,6 +447,8 @@ def _render_pass(ray_batch, feat_dy, feat_st, pts, z, s, t, frame_idx, offsets, 
     out["render_flows"] = flows
     out["s_vals"] = s
     out["exp_sf"] = exp_sf
+  if want_aux:
+    return out, out_dy, out_st, dict(coeff=coeff, raw_st=raw_st, m_st=m_st, ray_dir=ray_dir)
   return out, out_dy, out_st
 
 
@@ -459,20 +490,68 @@ def render_rays_mv(frame_idx, time_embedding, time_offset, ray_batch, model, pro
 def render_rays_mono(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, projector,
                      N_samples, args, inv_uniform=False, N_importance=0, raw_noise_std=0.0,
                      det=False, white_bkgd=False, is_train=True, num_vv=2, jitter=None):
-  """Coarse-only rendering for monocular video (render_ray.py:870-1277).
-  The training-only cross-time branch (:1099-1270) needs
-  autograd through the kernels and is not built yet."""
-  if is_train:
-    raise NotImplementedError("render_rays_mono(is_train=True): cross-time training branch "
-                              "(render_ray.py:1099-1270) is scheduled after the forward path")
+  """Coarse-only rendering for monocular video (render_ray.py:870-1277), including the
+  cross-time branch (:1099-1270) when is_train=True.  Forward only: the kernels have no
+  backward yet, so everything runs under no_grad (training needs SURVEY 8(f) f2)."""
   with torch.no_grad():
     t = _scalar(time_embedding[0].float())
     ray_batch, hb = _with_host_copies(ray_batch, model, ("trajectory_basis",))
+    basis = hb["trajectory_basis"]
+    fidx = int(frame_idx[0])
     pts, z, s = sample_along_camera_ray(ray_batch["ray_o"], ray_batch["ray_d"],
                                         ray_batch["depth_range"], N_samples, inv_uniform, det, jitter)
-    out, out_dy, out_st = _render_pass(ray_batch, featmaps[0], featmaps[2], pts, z, s, t,
-                                       int(frame_idx[0]), [int(o) for o in time_offset[0]], num_vv,
-                                       model.net_coarse_dy, model.net_coarse_st, model.motion_mlp,
-                                       hb["trajectory_basis"], 6, 1, want_vanilla_st=True)
-  return {"outputs_coarse": None, "outputs_fine": None, "outputs_coarse_ref": out,
-          "outputs_coarse_ref_dy": out_dy, "outputs_coarse_st": out_st}
+    out, out_dy, out_st, aux = _render_pass(ray_batch, featmaps[0], featmaps[2], pts, z, s, t, fidx,
+                                            [int(o) for o in time_offset[0]], num_vv,
+                                            model.net_coarse_dy, model.net_coarse_st, model.motion_mlp,
+                                            basis, 6, 1, want_vanilla_st=True, want_aux=True)
+    ret = {"outputs_coarse": None, "outputs_fine": None, "outputs_coarse_ref": out,
+           "outputs_coarse_ref_dy": out_dy, "outputs_coarse_st": out_st}
+    if is_train:
+      ret.update(_cross_time(ray_batch, featmaps[1], pts, z, aux, fidx, int(frame_idx[1]),
+                             _scalar(time_embedding[1].float()), [int(o) for o in time_offset[1]],
+                             num_vv, model, basis, args.occ_weights_mode, out, out_dy))
+  return ret
+
+
+def _cross_time(ray_batch, feat_anchor, pts, z, aux, ref_idx, anc_idx, t_anc, anchor_offsets, num_vv,
+                model, basis, occ_mode, out_ref, out_ref_dy):
+  """Cross-time rendering for temporal consistency (render_ray.py:1099-1270)."""
+  coeff = aux["coeff"]
+  sf_seq = traj_deltas(coeff, basis, [ref_idx + o for o in (-2, -1, 0, 1, 2, 3)],
+                       [ref_idx + o - 1 for o in (-2, -1, 0, 1, 2, 3)])
+  pts_anchor = displaced_points(pts, coeff, basis, ref_idx, [anc_idx - ref_idx])[0]  # :1109-1112
+  coeff_a = motion_coefficients(model.motion_mlp, pts_anchor, t_anc)                 # :1126-1127
+  seq_a = displaced_points(pts_anchor, coeff_a, basis, anc_idx, anchor_offsets, num_vv)  # :1149-1176
+  keep = [(i, anc_idx + o - ref_idx) for i, o in enumerate(anchor_offsets)
+          if -3 <= anc_idx + o - ref_idx <= 3]
+  pts_traj_anchor = seq_a[[i for i, _ in keep]]
+  pts_traj_ref = displaced_points(pts, coeff, basis, ref_idx, [ro for _, ro in keep])
+  cam = ray_batch["camera"]
+  V_a = ray_batch["anchor_src_cameras"].shape[1]
+  if PRECISION == _lib.PREC_BF16 and USE_FUSED and V_a <= 16:
+    raw_a, m_a = net_dynamic_fused(model.net_coarse_dy, pts_anchor, seq_a, aux["ray_dir"], cam,
+                                   ray_batch["anchor_src_rgbs"], ray_batch["anchor_src_cameras"],
+                                   featmaps_channels_last(feat_anchor), t_anc)
+  else:
+    f_a, _, m_a = project_gather(pts, seq_a, cam, ray_batch["anchor_src_rgbs"],
+                                 ray_batch["anchor_src_cameras"], feat_anchor)
+    raw_a = net_dynamic_forward(model.net_coarse_dy, pts_anchor, f_a, aux["ray_dir"], m_a, t_anc)
+  m_st = aux["m_st"]
+  # anchor samples count when ANY view sees them (render_ray.py:1198-1200)
+  out_a = _composite(raw_a, aux["raw_st"], z, m_a, V_a, 0, m_st, m_st.shape[2], 1)
+  out_a_dy = _composite_vanilla(raw_a, z, m_a, V_a, 0)
+  if occ_mode == 0:
+    key = "weights_dy" if abs(ref_idx - anc_idx) > 1 else "weights"
+  elif occ_mode == 1:
+    key = "weights_dy"
+  elif occ_mode == 2:
+    key = "weights"
+  else:
+    raise NotImplementedError
+  out_a["occ_weights"], out_a["occ_weight_map"] = occlusion_weights(out_ref[key], out_a[key])
+  out_a["pts_traj_ref"] = pts_traj_ref
+  out_a["pts_traj_anchor"] = pts_traj_anchor
+  out_a["sf_seq"] = sf_seq
+  out_a_dy["occ_weights"], out_a_dy["occ_weight_map"] = occlusion_weights(out_ref_dy["weights"],
+                                                                         out_a_dy["weights"])
+  return {"outputs_coarse_anchor": out_a, "outputs_coarse_anchor_dy": out_a_dy}

@@ -81,7 +81,7 @@ def time_offsets(V_dy, num_vv=0):
 
 
 def make_scene(H=288, W=512, V_dy=8, V_st=8, C=32, num_frames=24, frame_idx=10,
-               num_vv=0, seed=0, near=1.0, far=30.0, rays=None, stress=False):
+               num_vv=0, seed=0, near=1.0, far=30.0, rays=None, stress=False, anchor_offset=None):
   """Returns (ray_batch, featmaps_coarse, featmaps_fine, frame/time tuples).
   `rays`: None -> all H*W pixel rays; int n -> first n rays of a seeded
   permutation (keeps fixtures small)."""
@@ -109,6 +109,20 @@ def make_scene(H=288, W=512, V_dy=8, V_st=8, C=32, num_frames=24, frame_idx=10,
   frame = (frame_idx, None)
   t = (torch.tensor([frame_idx / num_frames], dtype=torch.float64), None)
   offs = (time_offsets(V_dy, num_vv), None)
+  if anchor_offset is not None:
+    # cross-time (training) inputs: a second set of dynamic source views around the
+    # anchor frame (train.py:264-281 builds featmaps[1] from `anchor_src_rgbs`)
+    _, _, cams_an, _ = make_cameras(H, W, V_dy, V_st, stress=False)
+    cams_an = cams_an.clone()
+    cams_an[0, :, 18 + 3] += 0.021  # shift the anchor rig a little in x
+    batch["anchor_src_rgbs"] = torch.rand(1, V_dy, H, W, 3, generator=g)
+    batch["anchor_src_cameras"] = cams_an
+    batch["anchor_camera"] = tgt
+    feat_c = (feat_c[0], torch.randn(V_dy, C, h4, w4, generator=g), feat_c[2])
+    a_idx = frame_idx + anchor_offset
+    frame = (frame_idx, a_idx)
+    t = (t[0], torch.tensor([a_idx / num_frames], dtype=torch.float64))
+    offs = (offs[0], time_offsets(V_dy, num_vv))
   return batch, feat_c, feat_f, frame, t, offs
 
 

@@ -112,6 +112,16 @@ int dyn_traj_displace(const float* pts, const float* coeff, const float* basis,
                       int n_off, int num_vv, int R, int S, float* pts_seq,
                       void* stream);
 
+/* ---- a16 helpers: cross-time branch of render_rays_mono, render_ray.py:1099-1270
+ * out[v] = traj(frames_a[v]) - traj(frames_b[v]) with traj(f) = sum_k coeff_k basis[f,k]
+ * (scene-flow sequence :1101-1105); frames_*_host are HOST arrays, n <= 8. */
+int dyn_traj_delta(const float* coeff, const float* basis, int T, int nb,
+                   const int* frames_a_host, const int* frames_b_host, int n,
+                   int R, int S, float* out, void* stream);
+/* occ [R,S] = 1 - |w_ref - w_anchor|, occ_map [R] = 1 - |sum_s (w_ref - w_anchor)| (:1224-1257) */
+int dyn_occlusion_weights(const float* w_ref, const float* w_anchor, int R, int S,
+                          float* occ, float* occ_map, void* stream);
+
 /* ---- a4-a6: Projector.compute_with_motions, projection.py:103-176 ---------
  * xyz_st [R,S,3]; xyz [V,R,S,3] or NULL (every view uses xyz_st: the static
  * branch, render_ray.py:498-500); query_cam [34]; src_rgbs [V,H,W,3]

@@ -622,26 +622,77 @@ def render_rays_mono(frame_idx, time_embedding, time_offset, ray_batch, model,
                      N_importance=0, raw_noise_std=0.0, det=False,
                      white_bkgd=False, is_train=True, num_vv=2, jitter=None,
                      return_aux=False):
-  """ibrnet/render_ray.py:870-1277 (reference-time branch; the training-only
-  cross-time branch :1099-1270 is SURVEY row a16, scheduled after the forward
-  path meets the bar)."""
-  if is_train:
-    raise NotImplementedError("cross-time branch (a16) not restated yet")
+  """ibrnet/render_ray.py:870-1277, including the training-only cross-time
+  branch :1099-1270 when is_train=True."""
   t = time_embedding[0]
   pts, z, s = sample_along_ray(ray_batch["ray_o"], ray_batch["ray_d"],
                                ray_batch["depth_range"], N_samples, inv_uniform,
                                None if det else jitter)
+  w_dy, w_st, w_mo = _sd(model.net_coarse_dy), _sd(model.net_coarse_st), _sd(model.motion_mlp)
+  shift = getattr(model.net_coarse_dy, "shift", 0.0)
   out, out_dy, out_st, aux = _pass(
       ray_batch, featmaps[0], featmaps[2], pts, z, s, t, frame_idx[0],
-      list(time_offset[0]), num_vv, _sd(model.net_coarse_dy),
-      _sd(model.net_coarse_st), _sd(model.motion_mlp), model.trajectory_basis,
-      args, getattr(model.net_coarse_dy, "shift", 0.0), flow_views=6, sf_k=1)
+      list(time_offset[0]), num_vv, w_dy, w_st, w_mo, model.trajectory_basis,
+      args, shift, flow_views=6, sf_k=1)
   ret = {"outputs_coarse": None, "outputs_fine": None,
          "outputs_coarse_ref": out, "outputs_coarse_ref_dy": out_dy,
          "outputs_coarse_st": out_st}
+  if is_train:
+    ret.update(_cross_time(ray_batch, featmaps[1], pts, z, aux, frame_idx, time_embedding,
+                           time_offset, num_vv, w_dy, w_mo, model.trajectory_basis, shift,
+                           args.occ_weights_mode, out, out_dy))
   if return_aux:
     ret["_aux"] = aux
   return ret
+
+
+def _cross_time(ray_batch, feat_anchor, pts, z, aux, frame_idx, time_embedding, time_offset,
+                num_vv, w_dy, w_mo, basis, shift, occ_mode, out_ref, out_ref_dy):
+  """Cross-time rendering for temporal consistency (render_ray.py:1099-1270)."""
+  ref_idx, anc_idx = frame_idx
+  t_anc = time_embedding[1]
+  traj = aux["traj"]
+  sf_seq = torch.stack([traj[o] - traj[o - 1] for o in (-2, -1, 0, 1, 2, 3)], 0)  # :1101-1105
+  pts_anchor = pts + (traj[anc_idx - ref_idx] - traj[0])  # :1109-1112
+  coeff_a = motion_coefficients(w_mo, pts_anchor, t_anc)  # :1126-1127
+  traj_a0 = traj_offset(coeff_a, basis[anc_idx])
+  seq_a, traj_ref_list, traj_anc_list = [], [], []
+  for off in time_offset[1]:  # :1149-1168
+    ref_off = anc_idx + off - ref_idx
+    tmp = pts_anchor + (traj_offset(coeff_a, basis[anc_idx + off]) - traj_a0)
+    seq_a.append(tmp)
+    if ref_off not in traj:
+      continue
+    traj_anc_list.append(tmp)
+    traj_ref_list.append(pts + traj[ref_off] - traj[0])
+  seq_a += [pts_anchor] * num_vv  # :1171-1172
+  seq_a = torch.stack(seq_a, 0)
+  f_a, _, m_a = project_gather(pts, seq_a, ray_batch["camera"], ray_batch["anchor_src_rgbs"],
+                               ray_batch["anchor_src_cameras"], feat_anchor)
+  pm_a = m_a[..., 0].sum(2) > 0  # :1198-1200
+  ray_dir = F.normalize(ray_batch["ray_d"], dim=-1)
+  raw_a = net_dynamic(w_dy, pts_anchor, f_a, ray_dir, m_a, t_anc, shift)
+  pm_st = aux["mask_st"][..., 0].sum(2) > 1
+  out_a = composite(raw_a, aux["raw_st"], z, pm_a, pm_st)
+  out_a_dy = composite_vanilla(raw_a, z, pm_a)
+  occ_dy = out_ref_dy["weights"] - out_a_dy["weights"]
+  if occ_mode == 0:  # :1232-1242
+    key = "weights_dy" if abs(ref_idx - anc_idx) > 1 else "weights"
+  elif occ_mode == 1:
+    key = "weights_dy"
+  elif occ_mode == 2:
+    key = "weights"
+  else:
+    raise NotImplementedError
+  occ = out_ref[key] - out_a[key]
+  out_a["occ_weights"] = 1.0 - occ.abs()
+  out_a["occ_weight_map"] = 1.0 - occ.sum(1).abs()
+  out_a["pts_traj_ref"] = torch.stack(traj_ref_list, 0)
+  out_a["pts_traj_anchor"] = torch.stack(traj_anc_list, 0)
+  out_a["sf_seq"] = sf_seq
+  out_a_dy["occ_weights"] = 1.0 - occ_dy.abs()
+  out_a_dy["occ_weight_map"] = 1.0 - occ_dy.sum(1).abs()
+  return {"outputs_coarse_anchor": out_a, "outputs_coarse_anchor_dy": out_a_dy}
 
 
 # -----------------------------------------------------------------------------

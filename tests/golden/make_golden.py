@@ -138,11 +138,15 @@ def main():
     P = ref.proj.Projector("cpu")
     fx = {"cfg": cfg, "checksum": checksum(batch, [feat_c, feat_f])}
     if cfg["mono"]:
+      train = cfg.get("anchor_offset") is not None
       ret = ref.rr.render_rays_mono(frame, t, offs, batch, mref, feat_c, P,
                                     cfg["N_samples"], args,
                                     inv_uniform=cfg["inv_uniform"], det=True,
-                                    is_train=False, num_vv=cfg["num_vv"])
-      for k in ("outputs_coarse_ref", "outputs_coarse_ref_dy", "outputs_coarse_st"):
+                                    is_train=train, num_vv=cfg["num_vv"])
+      keys = ("outputs_coarse_ref", "outputs_coarse_ref_dy", "outputs_coarse_st")
+      if train:
+        keys += ("outputs_coarse_anchor", "outputs_coarse_anchor_dy")
+      for k in keys:
         fx[k] = clean(ret[k])
     else:
       ret = ref.rr.render_rays_mv(frame, t, offs, batch, mref, P, feat_c, feat_f,

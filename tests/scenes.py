@@ -19,6 +19,11 @@ GOLDEN_CONFIGS = {
     "mono_small": dict(mono=True, H=36, W=64, V_dy=8, V_st=4, rays=24,
                        N_samples=32, N_importance=0, num_vv=2, inv_uniform=True,
                        anti_alias_pooling=1, mask_rgb=1, seed=13, stress=True),
+    # render_rays_mono(is_train=True): reference-time + cross-time (anchor) branch, row a16
+    "mono_train": dict(mono=True, H=36, W=64, V_dy=8, V_st=4, rays=20,
+                       N_samples=32, N_importance=0, num_vv=2, inv_uniform=True,
+                       anti_alias_pooling=1, mask_rgb=1, seed=14, stress=False,
+                       anchor_offset=2, occ_weights_mode=0),
 }
 
 
@@ -26,8 +31,9 @@ def build(cfg, sigma_bias=-4.0):
   batch, feat_c, feat_f, frame, t, offs = synthetic.make_scene(
       H=cfg["H"], W=cfg["W"], V_dy=cfg["V_dy"], V_st=cfg["V_st"],
       num_vv=cfg["num_vv"], seed=cfg["seed"], rays=cfg["rays"],
-      stress=cfg.get("stress", False))
-  args = synthetic.make_args(cfg["anti_alias_pooling"], cfg["mask_rgb"])
+      stress=cfg.get("stress", False), anchor_offset=cfg.get("anchor_offset"))
+  args = synthetic.make_args(cfg["anti_alias_pooling"], cfg["mask_rgb"],
+                             cfg.get("occ_weights_mode", 0))
   model, args = synthetic.make_model(cfg["N_samples"], cfg["N_importance"],
                                      args=args, seed=cfg["seed"],
                                      mono=cfg["mono"], sigma_bias=sigma_bias)

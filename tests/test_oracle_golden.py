@@ -45,11 +45,14 @@ def test_oracle_matches_golden(name, golden):
       "seeded inputs drifted from the ones the fixture was generated with"
   with torch.no_grad():
     if cfg["mono"]:
+      train = cfg.get("anchor_offset") is not None
       ret = orc.render_rays_mono(frame, t, offs, batch, model, feat_c, None,
                                  cfg["N_samples"], args, inv_uniform=cfg["inv_uniform"],
-                                 det=True, is_train=False, num_vv=cfg["num_vv"],
+                                 det=True, is_train=train, num_vv=cfg["num_vv"],
                                  return_aux=True)
       keys = ("outputs_coarse_ref", "outputs_coarse_ref_dy", "outputs_coarse_st")
+      if train:  # cross-time branch, render_ray.py:1099-1270
+        keys += ("outputs_coarse_anchor", "outputs_coarse_anchor_dy")
       aux = ret["_aux"]
     else:
       ret = orc.render_rays_mv(frame, t, offs, batch, model, None, feat_c, feat_f,

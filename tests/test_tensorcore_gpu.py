@@ -60,7 +60,7 @@ def test_linear_tc_is_exact_on_integers():
   assert torch.equal(got, x @ w.t())
 
 
-@pytest.mark.parametrize("name", ["mv_small", "mono_small"])
+@pytest.mark.parametrize("name", ["mv_small", "mono_small", "mono_train"])
 def test_bf16_mode_end_to_end(golden, name):
   from dynibar_b200 import render_ray as rr
   from dynibar_b200.projection import Projector
@@ -71,9 +71,10 @@ def test_bf16_mode_end_to_end(golden, name):
   d = lambda x: synthetic.to_device(x, DEV)
   with torch.no_grad():
     if cfg["mono"]:
+      train = cfg.get("anchor_offset") is not None
       want = orc.render_rays_mono(frame, t, offs, batch, model, feat_c, None, cfg["N_samples"], args,
-                                  inv_uniform=True, det=True, is_train=False, num_vv=cfg["num_vv"])
-      key = "outputs_coarse_ref"
+                                  inv_uniform=True, det=True, is_train=train, num_vv=cfg["num_vv"])
+      key = "outputs_coarse_anchor" if train else "outputs_coarse_ref"
     else:
       want = orc.render_rays_mv(frame, t, offs, batch, model, None, feat_c, feat_f, cfg["N_samples"],
                                 args, inv_uniform=True, N_importance=cfg["N_importance"], det=True,
@@ -84,8 +85,8 @@ def test_bf16_mode_end_to_end(golden, name):
   try:
     if cfg["mono"]:
       got = rr.render_rays_mono(frame, t, offs, d(batch), m, d(feat_c), Projector(DEV),
-                                cfg["N_samples"], args, inv_uniform=True, det=True, is_train=False,
-                                num_vv=cfg["num_vv"])
+                                cfg["N_samples"], args, inv_uniform=True, det=True,
+                                is_train=cfg.get("anchor_offset") is not None, num_vv=cfg["num_vv"])
     else:
       got = rr.render_rays_mv(frame, t, offs, d(batch), m, Projector(DEV), d(feat_c), d(feat_f),
                               cfg["N_samples"], args, inv_uniform=True,
