@@ -206,6 +206,10 @@ int dyn_featmaps_channels_last(const float* featmaps, float* out, int V, int C, 
   return launch_to_channels_last(featmaps, out, V, C, h * w, (cudaStream_t)stream);
 }
 
+static long long* g_view_dbg = nullptr;
+void dyn_debug_set_view_timestamps(long long* dev_buf) { g_view_dbg = dev_buf; }
+long long* view_dbg_ptr() { return g_view_dbg; }
+
 int dyn_net_static_fused(dyn_net_t net, const float* pts, const float* ray_o, const float* ray_d,
                          const float* query_cam, const float* src_rgbs, const float* src_cams,
                          const float* feat_cl, int R, int S, int V, int H, int W, int C, int h, int w,

@@ -113,15 +113,17 @@ __global__ void __launch_bounds__(320, 1) motion_fused_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
+  __shared__ __align__(16) FusedChunk s_tab[kMaxChunks];
+  stage_chunks(s_tab, a.chunks, a.nchunks);
   for (int i = tid; i < 2048; i += blockDim.x) cst[i] = a.params[a.o_bias[i >> 8] + (i & 255)];
   if (tid < 32) cst[2048 + tid] = tid < a.ncoef ? a.params[a.o_bias[8] + tid] : 0.f;
   const uint32_t tmem_base = fused_prologue(bars, tmem_slot, kPP);
   const int n_iter = (int)((a.N + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop<kPP>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 8) {
-    if ((tid & 31) == 0) issuer_loop<kPP>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
+    issuer_loop<kPP>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
     const int tile = tid >> 7, r = tid & 127;
     const int bt = kPP ? tile : 0;
@@ -184,15 +186,17 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
+  __shared__ __align__(16) FusedChunk s_tab[kMaxChunks];
+  stage_chunks(s_tab, a.chunks, a.nchunks);
   for (int i = tid; i < 256; i += blockDim.x) cst[i] = a.params[a.o_bgeo0 + i];
   for (int i = tid; i < 128; i += blockDim.x) cst[256 + i] = a.params[a.o_bgeo2 + i];
   const uint32_t tmem_base = fused_prologue(bars, tmem_slot, kPP);
   const int n_iter = (int)((a.P + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop<kPP>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 8) {
-    if ((tid & 31) == 0) issuer_loop<kPP>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
+    issuer_loop<kPP>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
     const int tile = tid >> 7, r = tid & 127;
     const int bt = kPP ? tile : 0;
@@ -299,6 +303,8 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
+  __shared__ __align__(16) FusedChunk s_tab[kMaxChunks];
+  stage_chunks(s_tab, a.chunks, a.nchunks);
   {
     const float* p = a.params;
     for (int i = tid; i < 128; i += blockDim.x) {
@@ -319,9 +325,9 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
   const int n_iter = (int)((a.P + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop<kPP>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 8) {
-    if ((tid & 31) == 0) issuer_loop<kPP>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
+    issuer_loop<kPP>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
     const int tile = tid >> 7, r = tid & 127;
     const int bt = kPP ? tile : 0;
@@ -477,6 +483,8 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
+  __shared__ __align__(16) FusedChunk s_tab[kMaxChunks];
+  stage_chunks(s_tab, a.chunks, a.nchunks);
   for (int i = tid; i < 64; i += blockDim.x) {
     cst[128 + i] = a.params[a.o_brgb2 + i];
     cst[192 + i] = a.params[a.o_wrgb4 + i];
@@ -486,9 +494,9 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
   const int n_iter = (int)((a.P * VP + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop<kPP>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 8) {
-    if ((tid & 31) == 0) issuer_loop<kPP>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
+    issuer_loop<kPP>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
     const int tile = tid >> 7, r = tid & 127;
     const int bt = kPP ? tile : 0;
@@ -602,6 +610,7 @@ static void upload(std::vector<uint8_t>& img, std::vector<FusedChunk>& tab, char
   out->img = cursor;
   out->tab = reinterpret_cast<const FusedChunk*>(cursor + img_bytes);
   out->nchunks = (int)tab.size();
+  if (tab.size() > (size_t)kMaxChunks) { *rc = fail(DYN_E_INVALID, "chunk table too long (%zu)", tab.size()); return; }
   cursor += need;
   left -= need;
   img.clear();

@@ -104,6 +104,17 @@ __device__ __forceinline__ void rs_step(const float* in, float* out, bool upper,
 }
 
 
+// The chunk table is staged into shared memory once per CTA: the producer and the issuer
+// read one entry per chunk on their critical path (a global load there costs an L2 round trip
+// per chunk and was the bottleneck of the MMA issue thread).
+constexpr int kMaxChunks = 160;
+__device__ __forceinline__ void stage_chunks(FusedChunk* s, const FusedChunk* __restrict__ g, int n) {
+  static_assert(sizeof(FusedChunk) == 16, "FusedChunk is copied as uint4");
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  uint4* dst = reinterpret_cast<uint4*>(s);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
 // ---- control warps (one elected lane each) -------------------------------------
 // barrier slots: [0..3] w_full, [4..7] w_empty, [8] a_ready(tile0), [9] acc_full(tile0),
 //                [10] a_ready(tile1), [11] acc_full(tile1)
@@ -132,7 +143,7 @@ __device__ __forceinline__ int round_end(const FusedChunk* __restrict__ chunks, 
   return c + 1 < nchunks ? c + 1 : nchunks;
 }
 
-template <bool PP>
+template <bool PP, int RING = kRing>
 __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chunks, int nchunks,
                                               const void* wimg, int n_iter, uint8_t* ring, uint32_t bar0) {
   const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(wimg);
@@ -142,8 +153,8 @@ __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chu
       const int c1 = PP ? round_end(chunks, c0, nchunks) : nchunks;
       for (int rep = 0; rep < (PP ? 2 : 1); ++rep) {
         for (int c = c0; c < c1; ++c, ++cnt) {
-          const uint32_t st = cnt % kRing;
-          if (cnt >= kRing) mbar_wait(bar0 + 8u * (4 + st), ((cnt / kRing) - 1) & 1);
+          const uint32_t st = cnt % RING;
+          if (cnt >= RING) mbar_wait(bar0 + 8u * (4 + st), ((cnt / RING) - 1) & 1);
           const FusedChunk ch = chunks[c];
           mbar_arrive_expect_tx(bar0 + 8u * st, ch.bytes);
           bulk_g2s(smem_u32(ring + st * kStageBytes), wsrc + ch.off, ch.bytes, bar0 + 8u * st);
@@ -154,14 +165,18 @@ __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chu
   }
 }
 
+// Called by ALL 32 lanes of the issuer warp (converged).
 // FusedChunk.flags: 1 = wait for a_ready before this chunk, 2 = last chunk of a
 // round (commit acc_full), 8 = first k-step overwrites D (start of a layer);
 // d_col = accumulator column offset inside the tile's 256-column TMEM region.
-template <bool PP>
+// NT = 128-row tiles per CTA (1 or 2), RING = weight-ring slots in use.
+template <bool PP, int NT = 2, int RING = kRing>
 __device__ __forceinline__ void issuer_loop(const FusedChunk* __restrict__ chunks, int nchunks, int n_iter,
                                             uint8_t* smem, uint8_t* ring, uint32_t bar0,
-                                            uint32_t tmem_base, int a_tile_bytes = kATileBytes) {
+                                            uint32_t tmem_base, int a_tile_bytes = kATileBytes,
+                                            long long* dbg = nullptr) {
   uint32_t cnt = 0, a_cnt[2] = {0, 0};
+  long long t_a = 0, t_w = 0, t_begin = clock64();
   const uint32_t a_addr[2] = {smem_u32(smem), smem_u32(smem + a_tile_bytes)};
   for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
     for (int c0 = 0; c0 < nchunks;) {
@@ -169,33 +184,54 @@ __device__ __forceinline__ void issuer_loop(const FusedChunk* __restrict__ chunk
       for (int rep = 0; rep < (PP ? 2 : 1); ++rep) {
         for (int c = c0; c < c1; ++c, ++cnt) {
           const FusedChunk ch = chunks[c];
+          long long t0 = dbg ? clock64() : 0;
           if (ch.flags & 1) {
             mbar_wait(bar_aready(bar0, PP ? rep : 0), a_cnt[PP ? rep : 0] & 1);
             ++a_cnt[PP ? rep : 0];
             tc_fence_after_sync();
           }
-          const uint32_t st = cnt % kRing;
-          mbar_wait(bar0 + 8u * st, (cnt / kRing) & 1);
+          long long t1 = dbg ? clock64() : 0;
+          const uint32_t st = cnt % RING;
+          mbar_wait(bar0 + 8u * st, (cnt / RING) & 1);
           tc_fence_after_sync();
-          const uint32_t idesc = idesc_bf16_f32(128, ch.npad);
-          const uint32_t w_addr = smem_u32(ring + st * kStageBytes);
-          const uint32_t lbo_b = (uint32_t)ch.npad * 16u;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (PP && t != rep) continue;
-            const uint32_t aa = a_addr[t] + (uint32_t)ch.a_kgroup * 2048u;
-            for (int ks = 0; ks < ch.ksteps; ++ks) {
-              mma_bf16_ss(tmem_base + t * 256 + ch.d_col, smem_desc(aa + ks * 4096u, 2048u, 128u),
-                          smem_desc(w_addr + ks * 2u * lbo_b, lbo_b, 128u), idesc,
-                          ((ch.flags & 8) && ks == 0) ? 0u : 1u);
-            }
+          long long t2 = 0;
+          if (dbg) {
+            t2 = clock64();
+            t_a += t1 - t0;
+            t_w += t2 - t1;
           }
-          mma_commit(bar0 + 8u * (4 + st));
-          if (ch.flags & 2) mma_commit(bar_acc(bar0, PP ? rep : 0));
+          // the whole warp runs the loop (warp-uniform values); one elected lane issues
+          if (elect_one()) {
+            const uint32_t idesc = idesc_bf16_f32(128, ch.npad);
+            const uint32_t w_addr = smem_u32(ring + st * kStageBytes);
+            const uint32_t lbo_b = (uint32_t)ch.npad * 16u;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+              if (PP && t != rep) continue;
+              const uint32_t aa = a_addr[t] + (uint32_t)ch.a_kgroup * 2048u;
+              for (int ks = 0; ks < ch.ksteps; ++ks) {
+                mma_bf16_ss(tmem_base + t * 256 + ch.d_col, smem_desc(aa + ks * 4096u, 2048u, 128u),
+                            smem_desc(w_addr + ks * 2u * lbo_b, lbo_b, 128u), idesc,
+                            ((ch.flags & 8) && ks == 0) ? 0u : 1u);
+              }
+            }
+            mma_commit(bar0 + 8u * (4 + st));
+            if (ch.flags & 2) mma_commit(bar_acc(bar0, PP ? rep : 0));
+          }
+          __syncwarp();
+          if (dbg && blockIdx.x == 0 && cnt < 120 && (threadIdx.x & 31) == 0) {
+            dbg[8 + 4 * cnt + 0] = t0; dbg[8 + 4 * cnt + 1] = t1;
+            dbg[8 + 4 * cnt + 2] = t2; dbg[8 + 4 * cnt + 3] = clock64();
+          }
         }
       }
       c0 = c1;
     }
+  }
+  if (dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    dbg[0] = clock64() - t_begin;  // issuer lifetime
+    dbg[1] = t_a;                  // waiting for A operands (epilogues)
+    dbg[2] = t_w;                  // waiting for weight chunks (ring)
   }
 }
 

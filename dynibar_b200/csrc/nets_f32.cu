@@ -10,6 +10,8 @@
 #include "nets.cuh"
 #include "nets_fused.cuh"
 
+extern "C" long long* view_dbg_ptr();
+
 namespace dyn {
 
 // ---------------------------------------------------------------------------
@@ -943,7 +945,7 @@ int net_static_fused(const dyn_net* n, const float* pts, const float* ray_o, con
                      float* raw, float* mask_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const StaticLayout& L = n->sl;
   const int prec = DYN_PREC_BF16;
-  ViewFusedArgs va;
+  ViewFusedArgs va{};
   RUN(fill_view_args(&va, query_cam, src_rgbs, src_cams, feat_cl, V, S, H, W, h, w, st));
   const int RC = net_rows_per_chunk(S, V);
   for (int r0 = 0; r0 < R_all; r0 += RC) {
@@ -961,6 +963,7 @@ int net_static_fused(const dyn_net* n, const float* pts, const float* ray_o, con
     va.ref_feat = d.reff; va.dfeat = nullptr;
     va.G = d.G; va.nvalid = d.t.nvalid; va.mask_proj = mask_out + p0 * V; va.mask_eff = d.meff;
     va.X = d.X; va.vis2 = d.vis2; va.ray_diff = d.rd; va.rgb_in = d.rgbin;
+    va.dbg = view_dbg_ptr();
     RUN(launch_view_fused(n, va, V, st));
     {
       Point2Args p2;
@@ -985,7 +988,7 @@ int net_dynamic_fused(const dyn_net* n, const float* pts, const float* pts_seq, 
                       int w, float* raw, float* mask_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const DynamicLayout& L = n->dl;
   const int prec = DYN_PREC_BF16;
-  ViewFusedArgs va;
+  ViewFusedArgs va{};
   RUN(fill_view_args(&va, query_cam, src_rgbs, src_cams, feat_cl, V, S, H, W, h, w, st));
   const long long P_all = (long long)R_all * S;
   const int RC = net_rows_per_chunk(S, V);

@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
+  __shared__ __align__(16) FusedChunk s_tab[kMaxChunks];
+  stage_chunks(s_tab, a.chunks, a.nchunks);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
   if (tid == 0) init_barriers(bar0, /*pp=*/true);
@@ -94,13 +96,13 @@ __global__ void __launch_bounds__(320, 1) view_fused_kernel(const __grid_constan
 
   const long long n_rows = a.P * VP;
   const int n_iter = (int)((n_rows + 255) / 256);
-  const FusedChunk* __restrict__ chunks = a.chunks;
+  const FusedChunk* chunks = s_tab;
   const int nchunks = a.nchunks;
 
   if (warp == 9) {
     if ((tid & 31) == 0) producer_loop<true>(chunks, nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == 8) {
-    if ((tid & 31) == 0) issuer_loop<true>(chunks, nchunks, n_iter, smem, ring, bar0, tmem_base);
+    issuer_loop<true>(chunks, nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
     // ------------------------- row threads -------------------------
     const int tile = tid >> 7, r = tid & 127;
@@ -532,6 +534,7 @@ int fused_view_build(dyn_net* n, const float* host_params, void* dst_dev, size_t
   n->fused_img = dst_dev;
   n->fused_tab = reinterpret_cast<char*>(dst_dev) + img_bytes;
   n->fused_nchunks = (int)tab.size();
+  if (tab.size() > (size_t)kMaxChunks) return fail(DYN_E_INVALID, "chunk table too long (%zu)", tab.size());
   return DYN_OK;
 }
 

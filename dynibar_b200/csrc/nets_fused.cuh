@@ -47,6 +47,8 @@ struct ViewFusedArgs {
   float* vis2;       // static [P*V]
   float* ray_diff;   // static [P*V,4]
   float* rgb_in;     // static [P*V,3] gathered source colours
+  int ablate;        // profiling only (DYN_ABLATE): 1 skip gather loads, 2 skip X/vis/mask stores, 4 skip pooled-output stores, 8 skip second pooling
+  long long* dbg;    // optional: clock64() phase timestamps of block 0 (profiling builds/tests only)
 };
 
 // ---- row-local fused chains (chains_fused.cu) ----

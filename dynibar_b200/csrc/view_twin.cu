@@ -12,6 +12,7 @@
 //   warps 0-7  : twin 0 of rows (tile = w >> 2, quadrant = w & 3)
 //   warps 8-15 : twin 1 of the same rows
 //   warp 16    : MMA issuer        warp 17 : weight producer
+#include <cstdlib>
 #include "fused_engine.cuh"
 #include "geometry.cuh"
 #include "nets.cuh"
@@ -28,7 +29,11 @@ constexpr int kTwinATile = 65536;  // K <= 256 in the per-view nets: 32 k-groups
 constexpr int T_B1 = 0, T_B2 = 256, T_B3 = 304, T_B4 = 560, T_B5 = 688, T_B6 = 816, T_W6V = 944,
               T_B7 = 1072, T_W8 = 1200, T_MISC = 1328, T_DFEAT = 1344, T_XCH = 1408;  // + 2 x 256 exchange
 constexpr int kTwinConst = T_XCH + 1024;
-constexpr int kSmemTwin = 2 * kTwinATile + kRing * kStageBytes + kTwinConst * 4 + 256;
+// NT = 128-row tiles per CTA: 2 -> one 576-thread CTA per SM (ping-pong between its tiles);
+// 1 -> two independent 320-thread CTAs per SM, each with one tile and a 2-slot weight ring, so
+// the tensor pipe is shared by two unsynchronised instruction streams.
+constexpr int twin_ring(int nt) { return nt == 1 ? 2 : kRing; }
+constexpr int twin_smem(int nt) { return nt * kTwinATile + twin_ring(nt) * kStageBytes + kTwinConst * 4 + 256; }
 
 __device__ __forceinline__ void pair_sync(int pair) {
   asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
@@ -62,17 +67,24 @@ __device__ __forceinline__ void elu_block_to_A(uint8_t* arow, uint32_t tacc, int
   }
 }
 
-template <int VP, bool ST>
-__global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant__ ViewFusedArgs a) {
+template <int VP, bool ST, int NT>
+__global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
+    view_twin_kernel(const __grid_constant__ ViewFusedArgs a) {
+  constexpr int ROWS = 128 * NT;          // rows per iteration
+  constexpr int RING = twin_ring(NT);
+  constexpr bool PP = (NT == 2) && kTwinPP;
+  constexpr int W_ISSUE = 8 * NT, W_PROD = 8 * NT + 1;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* ring = smem + 2 * kTwinATile;
-  float* cst = reinterpret_cast<float*>(ring + kRing * kStageBytes);
+  uint8_t* ring = smem + NT * kTwinATile;
+  float* cst = reinterpret_cast<float*>(ring + RING * kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(cst + kTwinConst);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
+  __shared__ __align__(16) FusedChunk s_tab[kMaxChunks];
+  stage_chunks(s_tab, a.chunks, a.nchunks);
 
-  if (tid == 0) init_barriers(bar0, kTwinPP, /*arrivals=*/256);
+  if (tid == 0) init_barriers(bar0, PP, /*arrivals=*/NT == 2 ? 256 : 128);
   {
     const float* prm = a.params;
     for (int i = tid; i < 256; i += blockDim.x) {
@@ -95,44 +107,51 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       cst[T_MISC + 2] = (ST && a.o_s >= 0) ? fabsf(prm[a.o_s]) : 0.f;
     }
   }
-  if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == W_ISSUE) tmem_alloc(smem_u32(tmem_slot), 256 * NT);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   const long long n_rows = a.P * VP;
-  const int n_iter = (int)((n_rows + 255) / 256);
+  const int n_iter = (int)((n_rows + ROWS - 1) / ROWS);
 
-  if (warp == 17) {
-    if ((tid & 31) == 0) producer_loop<kTwinPP>(a.chunks, a.nchunks, a.wimg, n_iter, ring, bar0);
-  } else if (warp == 16) {
-    if ((tid & 31) == 0)
-      issuer_loop<kTwinPP>(a.chunks, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kTwinATile);
+  if (warp == W_PROD) {
+    if ((tid & 31) == 0) producer_loop<PP, RING>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
+  } else if (warp == W_ISSUE) {
+    issuer_loop<PP, NT, RING>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kTwinATile,
+                           a.dbg ? a.dbg + 128 : nullptr);
   } else {
-    const int tw = tid >> 8;           // twin index
-    const int t = tid & 255;           // row slot inside the 256-row iteration
+    const int tw = tid / ROWS;         // twin index
+    const int t = tid % ROWS;          // row slot inside the iteration
     const int tile = t >> 7, r = t & 127;
     uint8_t* arow = smem + tile * kTwinATile + (r >> 3) * 128 + (r & 7) * 16;
     const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(tile * 256));
     const int v = t % VP;
     const int gl = t & (VP - 1);
-    const int pair = warp & 7;
-    const int bt = kTwinPP ? tile : 0;  // barrier tile
+    const int pair = warp & (4 * NT - 1);
+    const int bt = PP ? tile : 0;  // barrier tile
     float* xch5 = cst + T_XCH;        // [2][256] partial visibility logits of vis_fc
     float* xch7 = cst + T_XCH + 512;  // [2][256] partial logits of vis_fc2
     uint32_t acc_cnt = 0;
     const float wh = a.w_img, hh = a.h_img;
+    int dbg_n = 0;
+#define TS()                                                                            \
+  do {                                                                                  \
+    if (a.dbg != nullptr && blockIdx.x == 0 && t == 0 && dbg_n < 64)                 \
+      a.dbg[tw * 64 + dbg_n++] = clock64();                                             \
+  } while (0)
     constexpr int NG = ST ? 5 : (0);  // static: 5 channel groups per twin (set below for dynamic)
     (void)NG;
 
     for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
-      const long long pl = ((long long)it * 256 + t) / VP;
+      const long long pl = ((long long)it * ROWS + t) / VP;
       const bool pt_ok = pl < a.P;
       const bool valid = pt_ok && v < a.V;
       const long long m = pl * a.V + v;
       const long long ray = pt_ok ? pl / a.S : 0;
 
+      TS();  // 0: iteration start
       // ---- geometry (both twins; cheap) ----
       float p3[3] = {0.f, 0.f, 0.f}, q3[3];
       if (pt_ok) { p3[0] = a.pts[pl * 3]; p3[1] = a.pts[pl * 3 + 1]; p3[2] = a.pts[pl * 3 + 2]; }
@@ -194,12 +213,13 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
         mbar_arrive(bar_aready(bar0, bt));
       }
 
+      TS();  // 1: after F1 operand + arrive
       // ---- gather: rgb (both twins) + this twin's 16 feature channels ----
       float chv[40];  // this twin's pooled channels (layout in view_twin_build)
 #pragma unroll
       for (int i = 0; i < 40; ++i) chv[i] = 0.f;
       float rgb[3] = {0.f, 0.f, 0.f};
-      if (valid) {
+      if (valid && !(a.ablate & 1)) {
         const float gx = 2.f * pu / (wh - 1.f) - 1.f, gy = 2.f * pv / (hh - 1.f) - 1.f;
         {
           const float fx = (gx + 1.f) * 0.5f * (float)(a.w - 1), fy = (gy + 1.f) * 0.5f * (float)(a.h - 1);
@@ -212,20 +232,22 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
           for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
+              // out-of-range taps load a clamped texel with weight 0: no branch, so all 16
+              // tap loads of this thread are in flight together
               const int xi = x0 + dx, yi = y0 + dy;
-              const float wgt = (dx ? ax : bx) * (dy ? ay : by);
-              if (xi >= 0 && xi < a.w && yi >= 0 && yi < a.h) {
-                const float4* tp = reinterpret_cast<const float4*>(base + ((long long)yi * a.w + xi) * kC);
+              const bool in = xi >= 0 && xi < a.w && yi >= 0 && yi < a.h;
+              const float wgt = in ? (dx ? ax : bx) * (dy ? ay : by) : 0.f;
+              const int xc = min(max(xi, 0), a.w - 1), yc = min(max(yi, 0), a.h - 1);
+              const float4* tp = reinterpret_cast<const float4*>(base + ((long long)yc * a.w + xc) * kC);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float4 q = __ldg(tp + j);
-                  if (tw == 0) {
-                    chv[3 + 4 * j] += q.x * wgt; chv[4 + 4 * j] += q.y * wgt;
-                    chv[5 + 4 * j] += q.z * wgt; chv[6 + 4 * j] += q.w * wgt;
-                  } else {
-                    chv[4 * j] += q.x * wgt; chv[1 + 4 * j] += q.y * wgt;
-                    chv[2 + 4 * j] += q.z * wgt; chv[3 + 4 * j] += q.w * wgt;
-                  }
+              for (int j = 0; j < 4; ++j) {
+                const float4 q = __ldg(tp + j);
+                if (tw == 0) {
+                  chv[3 + 4 * j] += q.x * wgt; chv[4 + 4 * j] += q.y * wgt;
+                  chv[5 + 4 * j] += q.z * wgt; chv[6 + 4 * j] += q.w * wgt;
+                } else {
+                  chv[4 * j] += q.x * wgt; chv[1 + 4 * j] += q.y * wgt;
+                  chv[2 + 4 * j] += q.z * wgt; chv[3 + 4 * j] += q.w * wgt;
                 }
               }
             }
@@ -242,11 +264,11 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
               const int xi = x0 + dx, yi = y0 + dy;
-              const float wgt = (dx ? ax : bx) * (dy ? ay : by);
-              if (xi >= 0 && xi < a.W && yi >= 0 && yi < a.H) {
-                const float* tp = base + ((long long)yi * a.W + xi) * 3;
-                rgb[0] += __ldg(tp) * wgt; rgb[1] += __ldg(tp + 1) * wgt; rgb[2] += __ldg(tp + 2) * wgt;
-              }
+              const bool in = xi >= 0 && xi < a.W && yi >= 0 && yi < a.H;
+              const float wgt = in ? (dx ? ax : bx) * (dy ? ay : by) : 0.f;
+              const int xc = min(max(xi, 0), a.W - 1), yc = min(max(yi, 0), a.H - 1);
+              const float* tp = base + ((long long)yc * a.W + xc) * 3;
+              rgb[0] += __ldg(tp) * wgt; rgb[1] += __ldg(tp + 1) * wgt; rgb[2] += __ldg(tp + 2) * wgt;
             }
         }
       }
@@ -254,7 +276,7 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       if (ST && a.mask_rgb) mask *= ((rgb[0] + rgb[1] + rgb[2]) > 1e-3f) ? 1.f : 0.f;
       if (tw == 0) {
         chv[0] = rgb[0]; chv[1] = rgb[1]; chv[2] = rgb[2];
-        if (valid) {
+        if (valid && !(a.ablate & 2)) {
           a.mask_proj[m] = mask_proj;
           if (ST) {
             a.mask_eff[m] = mask;
@@ -264,16 +286,20 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
         }
       }
 
+      TS();  // 2: after gather
       if (ST) {
         // ---- F1 epilogue: this twin's 128 of the 256 columns ----
         mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+        TS();  // 3: F1 acc ready
         tc_fence_after_sync();
         elu_block_to_A<128>(arow, tacc, 128 * tw, cst + T_B1);
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(bar_aready(bar0, bt));
+        TS();  // 4: F1 epilogue done
         // ---- F2: src_feat (35 of 48 columns) * ref_feat; twin 0 keeps 0..17, twin 1 keeps 18..34 ----
         mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+        TS();  // 5: F2 acc ready
         tc_fence_after_sync();
         float s48[48];
         tmem_ld32(tacc, s48);
@@ -339,8 +365,10 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       tc_fence_before_sync();
       mbar_arrive(bar_aready(bar0, bt));
 
+      TS();  // 6: pool1 done + arrive
       // ---- F3: ELU(base_fc.0), this twin's 128 columns ----
       mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+      TS();  // 7: F3 acc ready
       tc_fence_after_sync();
       elu_block_to_A<128>(arow, tacc, 128 * tw, cst + T_B3);
       fence_proxy_async_smem();
@@ -348,8 +376,10 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       mbar_arrive(bar_aready(bar0, bt));
 
       const int c0 = 64 * tw;  // this twin's columns of the 128-wide layers
+      TS();  // 8: F3 epilogue done
       // ---- F4: x = ELU(base_fc.2) -> TMEM [128,256); A = x * w1 ----
       mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+      TS();  // 9: F4 acc ready
       tc_fence_after_sync();
 #pragma unroll 1
       for (int cb = c0; cb < c0 + 64; cb += 32) {
@@ -369,8 +399,10 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       tc_fence_before_sync();
       mbar_arrive(bar_aready(bar0, bt));
 
+      TS();  // 10: F4 epilogue done
       // ---- F5: h = ELU(vis_fc.0) -> A; partial visibility logit ----
       mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+      TS();  // 11: F5 acc ready
       tc_fence_after_sync();
       {
         float part = 0.f;
@@ -393,8 +425,10 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       tc_fence_before_sync();
       mbar_arrive(bar_aready(bar0, bt));
 
+      TS();  // 12: F5 epilogue done
       // ---- F6: x += ELU(vis_fc.2[:128]); A = x * vis1 ----
       mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+      TS();  // 13: F6 acc ready
       tc_fence_after_sync();
       // both twins arrived on a_ready before this MMA ran: the partial logits are visible
       const float vlogit = cst[T_MISC + 0] + xch5[t] + xch5[256 + t];
@@ -408,7 +442,7 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
 #pragma unroll
         for (int i = 0; i < 32; ++i) xs[i] += elu_fast(acc[i] + cst[T_B6 + cb + i]);
         tmem_st32(tacc + 128 + cb, xs);
-        if (ST && valid) {
+        if (ST && valid && !(a.ablate & 2)) {
           // spilled as bf16: its only consumer is the blending head's A operand
           uint4* xo = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.X) + m * 128 + cb);
 #pragma unroll
@@ -426,8 +460,10 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
       tc_fence_before_sync();
       mbar_arrive(bar_aready(bar0, bt));
 
+      TS();  // 14: F6 epilogue done
       // ---- F7: vis2 = sigmoid(vis_fc2.2 . ELU(vis_fc2.0)) * mask ----
       mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+      TS();  // 15: F7 acc ready
       tc_fence_after_sync();
       {
         float part = 0.f;
@@ -442,17 +478,18 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
         }
         xch7[tw * 256 + t] = part;
       }
+      TS();  // 16: F7 partial done
       pair_sync(pair);
       const float v2 = cst[T_MISC + 1] + xch7[t] + xch7[256 + t];
       const float vis2 = sigmoid_fast(v2) * mask;
-      if (ST && valid && tw == 0) a.vis2[m] = vis2;
+      if (ST && valid && tw == 0 && !(a.ablate & 2)) a.vis2[m] = vis2;
       const float vsum = group_sum<VP>(vis2);
       const float w2 = vis2 / (vsum + 1e-8f);
       const float W = group_sum<VP>(w2);
       const float nval = group_sum<VP>(mask);
 
       // ---- second pooling on this twin's 64 channels: reduce-scatter of sum(w x), sum(w x^2) ----
-      {
+      if (!(a.ablate & 8)) {
         const bool b0 = gl & 1, b1 = gl & 2, b2 = gl & 4, b3 = gl & 8;
         constexpr int NO = VP == 16 ? 4 : 8;
         const int cbase = c0 + (b0 ? 32 : 0) + (b1 ? 16 : 0) + (b2 ? 8 : 0) + ((VP == 16 && b3) ? 4 : 0);
@@ -485,7 +522,7 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
             for (int i = 0; i < NO; ++i) dst[i] = s3[i < 8 ? i : 0];
           }
         }
-        if (pt_ok) {
+        if (pt_ok && !(a.ablate & 4)) {
           float* g = a.G + pl * kGStride;
 #pragma unroll
           for (int i = 0; i < NO; ++i) {
@@ -499,13 +536,15 @@ __global__ void __launch_bounds__(576, 1) view_twin_kernel(const __grid_constant
           }
         }
       }
+      TS();  // 17: pool2 + outputs done
       tc_fence_before_sync();
     }
+#undef TS
   }
   __syncthreads();
-  if (warp == 16) {
+  if (warp == W_ISSUE) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256 * NT);
   }
 }
 
@@ -584,6 +623,7 @@ int view_twin_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes,
   n->twin.img = dst_dev;
   n->twin.tab = reinterpret_cast<const FusedChunk*>(reinterpret_cast<char*>(dst_dev) + img_bytes);
   n->twin.nchunks = (int)tab.size();
+  if (tab.size() > (size_t)kMaxChunks) return fail(DYN_E_INVALID, "chunk table too long (%zu)", tab.size());
   return DYN_OK;
 }
 
@@ -592,23 +632,31 @@ int launch_view_twin(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st)
   a.wimg = n->twin.img;
   a.chunks = n->twin.tab;
   a.nchunks = n->twin.nchunks;
+  { const char* e = getenv("DYN_ABLATE"); a.ablate = e ? atoi(e) : 0; }
   int dev = 0, sms = 148;
   DYN_CUDA(cudaGetDevice(&dev));
   DYN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int VP = V <= 8 ? 8 : 16;
-  const long long n_iter = (a.P * VP + 255) / 256;
-  const int grid = (int)(n_iter < sms ? n_iter : sms);
+  // DYN_VIEW_TILES=2 selects the one-CTA-per-SM ping-pong variant (kept for comparison)
+  const char* e_nt = getenv("DYN_VIEW_TILES");
+  const int nt = (e_nt && e_nt[0] == '2') ? 2 : 1;
+  const long long rows = 128LL * nt;
+  const long long n_iter = (a.P * VP + rows - 1) / rows;
+  const long long slots = (long long)sms * (nt == 1 ? 2 : 1);
+  const int grid = (int)(n_iter < slots ? n_iter : slots);
   if (grid == 0) return DYN_OK;
   const bool st_net = n->kind == DYN_NET_STATIC;
   ProfScope prof(st_net ? PROF_VIEW_ST : PROF_VIEW_DY, st);
-#define LAUNCH_VT(VPV, STV)                                                                  \
-  do {                                                                                       \
-    DYN_CUDA(cudaFuncSetAttribute(view_twin_kernel<VPV, STV>,                                \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTwin));  \
-    view_twin_kernel<VPV, STV><<<grid, 576, kSmemTwin, st>>>(a);                             \
+#define LAUNCH_VT(VPV, STV, NTV)                                                                 \
+  do {                                                                                           \
+    DYN_CUDA(cudaFuncSetAttribute(view_twin_kernel<VPV, STV, NTV>,                               \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, twin_smem(NTV))); \
+    view_twin_kernel<VPV, STV, NTV><<<grid, NTV * 256 + 64, twin_smem(NTV), st>>>(a);            \
   } while (0)
-  if (st_net) { if (VP == 8) LAUNCH_VT(8, true); else LAUNCH_VT(16, true); }
-  else { if (VP == 8) LAUNCH_VT(8, false); else LAUNCH_VT(16, false); }
+#define LAUNCH_VT2(VPV, STV) do { if (nt == 1) LAUNCH_VT(VPV, STV, 1); else LAUNCH_VT(VPV, STV, 2); } while (0)
+  if (st_net) { if (VP == 8) LAUNCH_VT2(8, true); else LAUNCH_VT2(16, true); }
+  else { if (VP == 8) LAUNCH_VT2(8, false); else LAUNCH_VT2(16, false); }
+#undef LAUNCH_VT2
 #undef LAUNCH_VT
   DYN_LAUNCH_CHECK();
   return DYN_OK;

@@ -234,6 +234,10 @@ int dyn_debug_point_chain(dyn_net_t net, const float* G, const float* nvalid,
                           float* out_a, float* out_b, float* posenc_ws,
                           void* stream);
 
+/* profiling hook: when set, block 0 of the fused static per-view kernel writes clock64()
+ * phase timestamps ([2 twins][64]) into dev_buf (profiles/scripts/prof_phases.py). */
+void dyn_debug_set_view_timestamps(long long* dev_buf);
+
 /* ---- building block: one nn.Linear on the tensor cores -----------------------
  * Y[M,N] = act(X[M,K] W[N,K]^T + b) with bf16 operands / fp32 accumulation
  * (tcgen05).  act: 0 none, 1 ELU, 2 ReLU, 3 sigmoid.  N <= 256.  packed_ws must
