@@ -489,7 +489,11 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
     cst[128 + i] = a.params[a.o_brgb2 + i];
     cst[192 + i] = a.params[a.o_wrgb4 + i];
   }
-  if (tid == 0) cst[256] = a.params[a.o_brgb4];
+  if (tid == 0) {
+    cst[256] = a.params[a.o_brgb4];
+    mbar_init(bar0 + 8u * 12, 1);
+    mbar_init(bar0 + 8u * 13, 1);
+  }
   const uint32_t tmem_base = fused_prologue(bars, tmem_slot, kPP);
   const int n_iter = (int)((a.P * VP + 255) / 256);
 
@@ -503,22 +507,23 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
     uint8_t* arow = smem + tile * kATileBytes + (r >> 3) * 128 + (r & 7) * 16;
     const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(tile * 256));
     const int v = tid % VP;
-    uint32_t acc_cnt = 0;
+    uint32_t acc_cnt = 0, x_cnt = 0;
+    const uint32_t xbar = bar0 + 8u * (12 + tile);  // x block of this tile has landed
+    const uint8_t* ximg = reinterpret_cast<const uint8_t*>(a.X);
+    const uint32_t atile = smem_u32(smem + tile * kATileBytes);
+    auto issue_x = [&](int it2) {
+      mbar_arrive_expect_tx(xbar, 32768u);
+      bulk_g2s(atile, ximg + ((size_t)it2 * 2 + tile) * 32768u, 32768u, xbar);
+    };
+    if (r == 0 && (int)blockIdx.x < n_iter) issue_x((int)blockIdx.x);
     for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
       const long long pl = ((long long)it * 256 + tid) / VP;
       const bool pt_ok = pl < a.P;
       const bool valid = pt_ok && v < a.V;
       const long long m = pl * a.V + v;
-      // operand: [x (128) | vis2, ray_diff (4) | 0 ...] = 144 columns
+      // operand: [x (128) | vis2, ray_diff (4) | 0 ...] = 144 columns; the x block is the tile image
+      // spilled by the per-view kernel and arrives by bulk copy (issued one iteration ahead)
       {
-        // x was spilled as bf16 by the per-view kernel: 16-byte chunks go straight into the tile
-        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.X) + m * 128);
-#pragma unroll 4
-        for (int g = 0; g < 16; ++g) {
-          uint4 q = make_uint4(0u, 0u, 0u, 0u);
-          if (valid) q = __ldg(src + g);
-          *reinterpret_cast<uint4*>(arow + g * 2048) = q;
-        }
         float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (valid) {
           const float4 rd = __ldg(reinterpret_cast<const float4*>(a.ray_diff) + m);
@@ -528,8 +533,12 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
         float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         store8(arow, 136, z);
       }
+      mbar_wait(xbar, x_cnt & 1); ++x_cnt;
       operand_ready(bar0, bt);
       wait_acc(bar0, bt, acc_cnt);  // rgb_fc.0: per-view part + per-point part GW (bias folded into GW)
+      // the MMA has consumed columns [0,144): prefetch the next iteration's x block behind it
+      // (the hidden layer below goes to columns [144,272) of the same tile)
+      if (r == 0 && it + (int)gridDim.x < n_iter) issue_x(it + (int)gridDim.x);
 #pragma unroll 1
       for (int cb = 0; cb < 128; cb += 32) {
         float acc[32];
@@ -543,7 +552,7 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
           acc[4 * i + 2] = elu_fast(acc[4 * i + 2] + q.z); acc[4 * i + 3] = elu_fast(acc[4 * i + 3] + q.w);
         }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
+        for (int g = 0; g < 4; ++g) store8(arow, 144 + cb + 8 * g, acc + 8 * g);
       }
       operand_ready(bar0, bt);
       wait_acc(bar0, bt, acc_cnt);  // rgb_fc.2 (64, ELU) -> rgb_fc.4 logit
@@ -695,7 +704,7 @@ int fused_chain_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_byte
     std::vector<int> m(144, -1);
     for (int i = 0; i < 133; ++i) m[i] = 128 + i;
     add(rgb0, 0, 128, 128, 144, m);
-    add(n->sl.rgb2, 0, 64, 64, 128, identity_map(128, 128));
+    add(n->sl.rgb2, 0, 64, 64, 128, identity_map(128, 128), 0, 18);  // hidden layer at columns [144,272)
     upload(img, tab, cur, left, &n->chain[2], st, &rc);
   }
   return rc;

@@ -104,6 +104,19 @@ __device__ __forceinline__ void rs_step(const float* in, float* out, bool upper,
 }
 
 
+// "Tile image": how bf16 activations travel between fused kernels through HBM.  Rows are grouped in
+// tiles of 128 and stored exactly as the consumer's UMMA A operand sits in shared memory (K-major
+// 8x8 core matrices): element (row r, column k) of a tile with KG 8-column groups lives at byte
+//   tile * KG * 2048 + (k / 8) * 2048 + (r % 128) * 16 + (k % 8) * 2.
+// The producer's per-row 16-byte stores are therefore warp-coalesced (32 rows x 16 B = 512 B), and
+// the consumer lands a whole operand block with ONE cp.async.bulk instead of per-thread loads.
+__host__ __device__ __forceinline__ size_t tile_image_off(long long row, int kgroup, int kgroups) {
+  return (size_t)(row >> 7) * (size_t)kgroups * 2048u + (size_t)kgroup * 2048u + (size_t)(row & 127) * 16u;
+}
+__host__ __device__ __forceinline__ size_t tile_image_bytes(long long rows, int kgroups) {
+  return (size_t)((rows + 127) >> 7) * (size_t)kgroups * 2048u;
+}
+
 // The chunk table is staged into shared memory once per CTA: the producer and the issuer
 // read one entry per chunk on their critical path (a global load there costs an L2 round trip
 // per chunk and was the bottleneck of the MMA issue thread).

@@ -860,7 +860,11 @@ static size_t fused_alloc(Bump& b, bool st_net, int R, int S, int V, FusedBufs* 
   d->sh = b.f(P * 128); d->sig = b.f(P);
   if (st_net) {
     d->refpl = b.f((long long)R * 6); d->refpe = b.f((long long)R * 66); d->reff = b.f((long long)R * kF);
-    d->X = b.f(M * 128); d->vis2 = b.f(M); d->rd = b.f(M * 4); d->meff = b.f(M); d->rgbin = b.f(M * 3);
+    {  // x spill: bf16 tile image over view SLOTS (VP per point), padded to the kernels' 256-row iterations
+      const long long slots = ((P * (V <= 8 ? 8 : 16) + 255) / 256) * 256;
+      d->X = b.f(slots * 64);
+    }
+    d->vis2 = b.f(M); d->rd = b.f(M * 4); d->meff = b.f(M); d->rgbin = b.f(M * 3);
     d->ch = b.f(M * 128); d->ch2 = b.f(M * 64); d->logit = b.f(M);
   } else {
     d->ptspe = b.f(P * 33); d->dirpe = b.f((long long)R * 27);

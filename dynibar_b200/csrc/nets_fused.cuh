@@ -102,7 +102,7 @@ struct Point2Args {
 };
 
 struct RgbHeadArgs {
-  const float *X /* bf16 [P*V,128] */, *vis2, *ray_diff, *mask_eff, *rgb_in, *GW, *sigma;
+  const float *X /* bf16 tile image, 16 k-groups, rows = view slots (point * VP + view) */, *vis2, *ray_diff, *mask_eff, *rgb_in, *GW, *sigma;
   long long P;
   int V;
   float* raw;  // [P,4]

@@ -442,13 +442,15 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
 #pragma unroll
         for (int i = 0; i < 32; ++i) xs[i] += elu_fast(acc[i] + cst[T_B6 + cb + i]);
         tmem_st32(tacc + 128 + cb, xs);
-        if (ST && valid && !(a.ablate & 2)) {
-          // spilled as bf16: its only consumer is the blending head's A operand
-          uint4* xo = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.X) + m * 128 + cb);
+        if (ST && !(a.ablate & 2)) {
+          // spilled as a bf16 tile image (fused_engine.cuh) in view-slot row order: the blending
+          // head lands it in its operand tile with one bulk copy per 128 rows
+          uint8_t* xo = reinterpret_cast<uint8_t*>(a.X) + tile_image_off((long long)it * ROWS + t, cb >> 3, 16);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            xo[i] = make_uint4(pack_bf16x2(xs[8 * i], xs[8 * i + 1]), pack_bf16x2(xs[8 * i + 2], xs[8 * i + 3]),
-                               pack_bf16x2(xs[8 * i + 4], xs[8 * i + 5]), pack_bf16x2(xs[8 * i + 6], xs[8 * i + 7]));
+            *reinterpret_cast<uint4*>(xo + i * 2048) =
+                make_uint4(pack_bf16x2(xs[8 * i], xs[8 * i + 1]), pack_bf16x2(xs[8 * i + 2], xs[8 * i + 3]),
+                           pack_bf16x2(xs[8 * i + 4], xs[8 * i + 5]), pack_bf16x2(xs[8 * i + 6], xs[8 * i + 7]));
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) xs[i] *= vis1;
