@@ -1,14 +1,15 @@
 // Ray-transformer attention on tcgen05 (a11: ibrnet/mlp_network.py:13-31, :84-98).
 //
-// One CTA = one 128-row tile = 128/S whole rays (S | 128).  Q, K, V rows are
-// converted to bf16 and laid out as canonical K-major tiles in shared memory;
+// One CTA = one 128-row tile = 128/S whole rays (S | 128).  Q, K, V arrive as bf16 tile
+// images (fused_engine.cuh; written by point1_fused_kernel) and are landed in shared memory
+// by bulk copies (K, V: 32 KB each per tile; Q: one 8 KB head slice at a time);
 // per head h:  logits = Q_h K_h^T  (UMMA 128x128x32, fp32 in TMEM columns [0,128))
 //              softmax over the keys of the row's own ray, in registers
 //              (query rows with <= 1 valid view attend uniformly: the reference
 //               masks QUERY rows, mlp_network.py:23-24, :91-94)
 //              O_h = P V_h        (UMMA 128x32x128; P is written back to smem as the
 //               A operand, V_h is read in place as an MN-major B operand)
-// O (fp32, TMEM columns [128,256)) is written to global at the end.
+// O (fp32, TMEM columns [128,256)) is written to global at the end, again as a bf16 tile image.
 #include "nets.cuh"
 #include "tc.cuh"
 
@@ -28,27 +29,6 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32_bmn(int M, int N) {
   return idesc_bf16_f32(M, N) | (1u << 16);
 }
 
-// Warp-cooperative load of this warp's 32 rows of a [*,128] fp32 matrix into the
-// canonical bf16 tile.  Per instruction pair a warp covers 8 rows x 32 columns:
-// lane l -> row (l % 8), k-group (l / 8): 128 contiguous bytes per row in global
-// memory (rows are already bf16), and the 8 lanes of every quarter-warp hit 8 different 16-byte rows of one
-// core matrix in shared memory (conflict-free STS.128).
-__device__ __forceinline__ void warp_rows_to_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ src,
-                                                  long long row0, long long P, int warp, int lane) {
-#pragma unroll
-  for (int rg = 0; rg < 4; ++rg) {
-    const int r = warp * 32 + rg * 8 + (lane & 7);
-    const long long row = row0 + r;
-#pragma unroll
-    for (int kq = 0; kq < 4; ++kq) {
-      const int kg = kq * 4 + (lane >> 3);
-      uint4 q = make_uint4(0u, 0u, 0u, 0u);
-      if (row < P) q = __ldg(reinterpret_cast<const uint4*>(src + row * 128 + kg * 8));
-      *reinterpret_cast<uint4*>(tile + kg * 2048 + (r >> 3) * 128 + (r & 7) * 16) = q;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(128, 2)
 attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K,
                     const __nv_bfloat16* __restrict__ V, const float* __restrict__ nvalid, long long P, int S,
@@ -62,7 +42,11 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar_s = smem_u32(bars), bar_o = smem_u32(bars + 1);
-  if (tid == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_fence_init(); }
+  const uint32_t bar_kv = smem_u32(bars + 2), bar_q = smem_u32(bars + 3);
+  if (tid == 0) {
+    mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_kv, 1); mbar_init(bar_q, 1);
+    mbar_fence_init();
+  }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
   tc_fence_before_sync();
   __syncthreads();
@@ -78,45 +62,49 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
   const int warp_lo = ((warp * 32) / S) * S;
   const int warp_hi = ((warp * 32 + 31) / S + 1) * S;
   const float scale = 0.17677669529663687f;  // 1 / sqrt(32)
-  uint32_t ph_s = 0, ph_o = 0;
+  uint32_t ph_s = 0, ph_o = 0, ph_kv = 0, ph_q = 0;
+  const uint8_t* qimg = reinterpret_cast<const uint8_t*>(Q);
+  const uint8_t* kimg = reinterpret_cast<const uint8_t*>(K);
+  const uint8_t* vimg = reinterpret_cast<const uint8_t*>(V);
+
+  // thread 0 issues every bulk copy; the MMAs are issued by an elected lane of warp 0 with the
+  // whole warp converged (descriptors then stay in uniform registers)
+  auto issue_qk = [&](int h) {  // all lanes of warp 0: logits_h = Q_h K_h^T (waits for the Q_h slice)
+    mbar_wait(bar_q, ph_q & 1); ++ph_q;
+    tc_fence_after_sync();
+    if (elect_one()) {
+      const uint32_t idesc = idesc_bf16_f32(128, 128);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma_bf16_ss(tmem_base, smem_desc(smem_u32(qt) + (2 * ks) * 2048u, 2048u, 128u),
+                    smem_desc(smem_u32(kt) + (4 * h + 2 * ks) * 2048u, 2048u, 128u), idesc, ks ? 1u : 0u);
+      mma_commit(bar_s);
+    }
+    __syncwarp();
+  };
+  auto load_q = [&](long long tile, int h) {  // head slice: k-groups 4h..4h+3 are contiguous in the image
+    mbar_arrive_expect_tx(bar_q, (uint32_t)kQSlice);
+    bulk_g2s(smem_u32(qt), qimg + (size_t)tile * kTile + (size_t)h * kQSlice, (uint32_t)kQSlice, bar_q);
+  };
 
   const long long n_tiles = (P + 127) / 128;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row = tile * 128 + r;
     const bool ok = row < P;
-    warp_rows_to_tile(kt, K, tile * 128, P, warp, tid & 31);
-    warp_rows_to_tile(vt, V, tile * 128, P, warp, tid & 31);
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_kv, 2u * kTile);
+      bulk_g2s(smem_u32(kt), kimg + (size_t)tile * kTile, (uint32_t)kTile, bar_kv);
+      bulk_g2s(smem_u32(vt), vimg + (size_t)tile * kTile, (uint32_t)kTile, bar_kv);
+      load_q(tile, 0);
+    }
     const bool q_valid = ok && nvalid[row] > 1.f;
-    // this row's Q_h (32 values) packed for head 0; later heads are prefetched during the softmax
-    uint4 qreg[4];
-    auto load_q = [&](int h) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        qreg[g] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok) qreg[g] = __ldg(reinterpret_cast<const uint4*>(Q + row * 128 + h * 32 + g * 8));
-      }
-    };
-    load_q(0);
+    mbar_wait(bar_kv, ph_kv & 1); ++ph_kv;
+    if (warp == 0) issue_qk(0);
     for (int h = 0; h < 4; ++h) {
-      // Q_h slice (the previous head's QK^T finished: every thread waited on bar_s)
-#pragma unroll
-      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(qt + roff + g * 2048) = qreg[g];
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after_sync();
-        const uint32_t idesc = idesc_bf16_f32(128, 128);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          mma_bf16_ss(tmem_base, smem_desc(smem_u32(qt) + (2 * ks) * 2048u, 2048u, 128u),
-                      smem_desc(smem_u32(kt) + (4 * h + 2 * ks) * 2048u, 2048u, 128u), idesc, ks ? 1u : 0u);
-        mma_commit(bar_s);
-      }
-      if (h < 3) load_q(h + 1);
       mbar_wait(bar_s, ph_s & 1);
       ++ph_s;
       tc_fence_after_sync();
+      if (tid == 0 && h < 3) load_q(tile, h + 1);  // Q_h has been consumed
       // ---- softmax over this row's ray (keys [ray_lo, ray_lo + S)) ----
       float mx = -INFINITY;
 #pragma unroll 1
@@ -159,27 +147,25 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
           *reinterpret_cast<uint4*>(pt + roff + ((cb >> 3) + g) * 2048) = q;
         }
       }
-      const float inv = 1.f / den;
-      // O_h needs 1/den per row: stash it in registers via a small array indexed by h
-      // (written out in the final pass) -> keep as 4 scalars
-      if (h == 0) reinterpret_cast<float*>(bars + 8)[r * 4 + 0] = inv;
-      if (h == 1) reinterpret_cast<float*>(bars + 8)[r * 4 + 1] = inv;
-      if (h == 2) reinterpret_cast<float*>(bars + 8)[r * 4 + 2] = inv;
-      if (h == 3) reinterpret_cast<float*>(bars + 8)[r * 4 + 3] = inv;
+      reinterpret_cast<float*>(bars + 8)[r * 4 + h] = 1.f / den;  // applied when O is written out
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
+      __syncthreads();  // P complete; every thread is done reading logits_h
+      if (warp == 0) {
         tc_fence_after_sync();
-        const uint32_t idesc = idesc_bf16_f32_bmn(128, 32);
+        if (elect_one()) {
+          const uint32_t idesc = idesc_bf16_f32_bmn(128, 32);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          mma_bf16_ss(tmem_base + 128 + 32 * h, smem_desc(smem_u32(pt) + ks * 4096u, 2048u, 128u),
-                      // V_h as MN-major B: n = d in [32h, 32h+32) -> n-groups at stride 2048 (SBO),
-                      // k = key -> k-groups at stride 128 (LBO); this k-step covers keys [16ks, 16ks+16)
-                      smem_desc(smem_u32(vt) + (4 * h) * 2048u + ks * 256u, 128u, 2048u), idesc,
-                      ks ? 1u : 0u);
-        mma_commit(bar_o);
+          for (int ks = 0; ks < 8; ++ks)
+            mma_bf16_ss(tmem_base + 128 + 32 * h, smem_desc(smem_u32(pt) + ks * 4096u, 2048u, 128u),
+                        // V_h as MN-major B: n = d in [32h, 32h+32) -> n-groups at stride 2048 (SBO),
+                        // k = key -> k-groups at stride 128 (LBO); this k-step covers keys [16ks, 16ks+16)
+                        smem_desc(smem_u32(vt) + (4 * h) * 2048u + ks * 256u, 128u, 2048u), idesc,
+                        ks ? 1u : 0u);
+          mma_commit(bar_o);
+        }
+        __syncwarp();
+        if (h < 3) issue_qk(h + 1);  // queued behind P V_h; overlaps the next softmax's wait
       }
     }
     mbar_wait(bar_o, ph_o & 1);
@@ -193,10 +179,10 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
       tmem_wait_ld();
       if (ok) {
         const float inv = invs[h];
-        uint4* dst = reinterpret_cast<uint4*>(O + row * 128 + 32 * h);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(O) + (size_t)tile * kTile + (size_t)(4 * h) * 2048 + (size_t)r * 16;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          dst[i] = make_uint4(pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv),
+          *reinterpret_cast<uint4*>(dst + i * 2048) = make_uint4(pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv),
                               pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
                               pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv),
                               pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv));

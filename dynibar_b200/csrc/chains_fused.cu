@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
   stage_chunks(s_tab, a.chunks, a.nchunks);
   for (int i = tid; i < 256; i += blockDim.x) cst[i] = a.params[a.o_bgeo0 + i];
   for (int i = tid; i < 128; i += blockDim.x) cst[256 + i] = a.params[a.o_bgeo2 + i];
+  if (tid == 0) { mbar_init(bar0 + 8u * 12, 1); mbar_init(bar0 + 8u * 13, 1); }
   const uint32_t tmem_base = fused_prologue(bars, tmem_slot, kPP);
   const int n_iter = (int)((a.P + 255) / 256);
 
@@ -202,26 +203,21 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
     const int bt = kPP ? tile : 0;
     uint8_t* arow = smem + tile * kATileBytes + (r >> 3) * 128 + (r & 7) * 16;
     const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(tile * 256));
-    uint32_t acc_cnt = 0;
+    uint32_t acc_cnt = 0, g_cnt = 0;
+    const uint32_t gbar = bar0 + 8u * (12 + tile);  // this tile's G block has landed
+    const uint8_t* gimg = reinterpret_cast<const uint8_t*>(a.G);
+    const uint32_t atile = smem_u32(smem + tile * kATileBytes);
+    auto issue_g = [&](int it2) {
+      mbar_arrive_expect_tx(gbar, (uint32_t)kATileBytes);
+      bulk_g2s(atile, gimg + ((size_t)it2 * 2 + tile) * (size_t)kATileBytes, (uint32_t)kATileBytes, gbar);
+    };
+    if (r == 0 && (int)blockIdx.x < n_iter) issue_g((int)blockIdx.x);
     for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
       const long long row = (long long)it * 256 + tid;
       const bool valid = row < a.P;
-      // operand: G row (257 of 272 columns)
-      {
-        const float4* src = reinterpret_cast<const float4*>(a.G + row * kGStride);
-#pragma unroll 4
-        for (int g = 0; g < 34; ++g) {
-          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (valid) {
-            const float4 q0 = __ldg(src + 2 * g), q1 = __ldg(src + 2 * g + 1);
-            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
-            v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-            if (g == 32) { v[1] = v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = 0.f; }
-            if (g == 33) { v[0] = 0.f; v[1] = v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = 0.f; }
-          }
-          store8(arow, 8 * g, v);
-        }
-      }
+      // operand: the pooled statistics G arrive as a ready-made tile image (written by the
+      // per-view kernel): one 68 KB bulk copy per 128 points, issued one iteration ahead
+      mbar_wait(gbar, g_cnt & 1); ++g_cnt;
       operand_ready(bar0, bt);
       wait_acc(bar0, bt, acc_cnt);  // geometry_fc.0
       epi_cols_to_A<1>(arow, tacc, 256, cst);
@@ -240,10 +236,11 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
             if (a.posenc) v += __ldg(a.posenc + s_idx * 128 + cb + i);
             acc[i] = v;
           }
-          if (valid) {
-            float4* o = reinterpret_cast<float4*>(a.g2 + row * 128 + cb);
+          if (valid) {  // residual stream, fp32 tile layout (fused_engine.cuh: tile_f32_off)
+            uint8_t* o = reinterpret_cast<uint8_t*>(a.g2) + tile_f32_off(row, cb >> 2);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(o + i * 2048) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
@@ -256,28 +253,37 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
         float acc[32];
         tmem_ld32(tacc + cb, acc);
         tmem_wait_ld();
-        if (valid) {
-          __nv_bfloat16* base = (cb < 128 ? a.Q : a.K) + row * 128 + (cb & 127);
-          uint4* o = reinterpret_cast<uint4*>(base);
+        {  // Q / K as bf16 tile images (16 k-groups), the attention kernel's operands; rows past
+           // the last point are written as zeros (the attention reads whole 128-row tiles)
+          if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+          }
+          uint8_t* o = reinterpret_cast<uint8_t*>(cb < 128 ? a.Q : a.K) + tile_image_off(row, (cb & 127) >> 3, 16);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            o[i] = make_uint4(pack_bf16x2(acc[8 * i], acc[8 * i + 1]), pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]),
+            *reinterpret_cast<uint4*>(o + i * 2048) = make_uint4(pack_bf16x2(acc[8 * i], acc[8 * i + 1]), pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]),
                               pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]), pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7]));
         }
       }
       tc_fence_before_sync();
       mbar_arrive(bar_aready(bar0, bt));  // operand unchanged; accumulators are free again
       wait_acc(bar0, bt, acc_cnt);     // Wv
+      if (r == 0 && it + (int)gridDim.x < n_iter) issue_g(it + (int)gridDim.x);  // operand tile is free
 #pragma unroll 1
       for (int cb = 0; cb < 128; cb += 32) {
         float acc[32];
         tmem_ld32(tacc + cb, acc);
         tmem_wait_ld();
-        if (valid) {
-          uint4* o = reinterpret_cast<uint4*>(a.V + row * 128 + cb);
+        {
+          if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+          }
+          uint8_t* o = reinterpret_cast<uint8_t*>(a.V) + tile_image_off(row, cb >> 3, 16);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            o[i] = make_uint4(pack_bf16x2(acc[8 * i], acc[8 * i + 1]), pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]),
+            *reinterpret_cast<uint4*>(o + i * 2048) = make_uint4(pack_bf16x2(acc[8 * i], acc[8 * i + 1]), pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]),
                               pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]), pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7]));
         }
       }
@@ -319,7 +325,11 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
       for (int i = tid; i < 192; i += blockDim.x) cst[1088 + i] = p[a.o_wrgb4 + i];
       if (tid < 3) cst[1281 + tid] = p[a.o_brgb4 + tid];
     }
-    if (tid == 0) cst[1280] = p[a.o_boutgeo2];
+    if (tid == 0) {
+      cst[1280] = p[a.o_boutgeo2];
+      mbar_init(bar0 + 8u * 12, 1);
+      mbar_init(bar0 + 8u * 13, 1);
+    }
   }
   const uint32_t tmem_base = fused_prologue(bars, tmem_slot, kPP);
   const int n_iter = (int)((a.P + 255) / 256);
@@ -333,20 +343,20 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
     const int bt = kPP ? tile : 0;
     uint8_t* arow = smem + tile * kATileBytes + (r >> 3) * 128 + (r & 7) * 16;
     const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(tile * 256));
-    uint32_t acc_cnt = 0;
+    uint32_t acc_cnt = 0, o_cnt = 0;
+    const uint32_t obar = bar0 + 8u * (12 + tile);
+    const uint8_t* oimg = reinterpret_cast<const uint8_t*>(a.O);
+    const uint32_t atile = smem_u32(smem + tile * kATileBytes);
+    auto issue_o = [&](int it2) {
+      mbar_arrive_expect_tx(obar, 32768u);
+      bulk_g2s(atile, oimg + ((size_t)it2 * 2 + tile) * 32768u, 32768u, obar);
+    };
+    if (r == 0 && (int)blockIdx.x < n_iter) issue_o((int)blockIdx.x);
     for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
       const long long row = (long long)it * 256 + tid;
       const bool valid = row < a.P;
-      // operand: attention output O (128 bf16): 16-byte chunks go straight into the tile
-      {
-        const uint4* src = reinterpret_cast<const uint4*>(a.O + row * 128);
-#pragma unroll 4
-        for (int g = 0; g < 16; ++g) {
-          uint4 q = make_uint4(0u, 0u, 0u, 0u);
-          if (valid) q = __ldg(src + g);
-          *reinterpret_cast<uint4*>(arow + g * 2048) = q;
-        }
-      }
+      // operand: attention output O, a bf16 tile image: one 32 KB bulk copy per 128 points
+      mbar_wait(obar, o_cnt & 1); ++o_cnt;
       operand_ready(bar0, bt);
       wait_acc(bar0, bt, acc_cnt);  // fc (no bias) + residual, LayerNorm (eps 1e-6) via TMEM scratch
       {
@@ -356,10 +366,10 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
           float acc[32];
           tmem_ld32(tacc + cb, acc);
           tmem_wait_ld();
-          const float4* res = reinterpret_cast<const float4*>(a.g2 + row * 128 + cb);
+          const uint8_t* res = reinterpret_cast<const uint8_t*>(a.g2) + tile_f32_off(row, cb >> 2);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float4 q = valid ? __ldg(res + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 q = valid ? __ldg(reinterpret_cast<const float4*>(res + i * 2048)) : make_float4(0.f, 0.f, 0.f, 0.f);
             acc[4 * i] += q.x; acc[4 * i + 1] += q.y; acc[4 * i + 2] += q.z; acc[4 * i + 3] += q.w;
           }
 #pragma unroll
@@ -422,10 +432,12 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
           sigma = fmaf(elu_fast(acc[i] + cst[640 + cb + i]), cst[768 + cb + i], sigma);
       }
       const float nv = valid ? a.nvalid[row] : 0.f;
+      if (!DYNAMIC && r == 0 && it + (int)gridDim.x < n_iter) issue_o(it + (int)gridDim.x);  // last MMA round is done
       if (DYNAMIC) {
         epi_cols_to_A<1>(arow, tacc + 128, 128, cst + 896);  // ELU(rgb_fc.0) -> operand
         operand_ready(bar0, bt);
         wait_acc(bar0, bt, acc_cnt);  // rgb_fc.2 (64) -> rgb_fc.4 (3) as dot products
+        if (r == 0 && it + (int)gridDim.x < n_iter) issue_o(it + (int)gridDim.x);
         float c3[3] = {cst[1281], cst[1282], cst[1283]};
 #pragma unroll 1
         for (int cb = 0; cb < 64; cb += 32) {
@@ -453,11 +465,11 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
           float acc[32];
           tmem_ld32(tacc + 128 + cb, acc);
           tmem_wait_ld();
-          if (valid) {
-            float4* o = reinterpret_cast<float4*>(a.GW + row * 128 + cb);
+          if (valid) {  // fp32 tile layout, read per (point, view) row by the blending head
+            uint8_t* o = reinterpret_cast<uint8_t*>(a.GW) + tile_f32_off(row, cb >> 2);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              o[i] = make_float4(acc[4 * i] + cst[896 + cb + 4 * i], acc[4 * i + 1] + cst[896 + cb + 4 * i + 1],
+              *reinterpret_cast<float4*>(o + i * 2048) = make_float4(acc[4 * i] + cst[896 + cb + 4 * i], acc[4 * i + 1] + cst[896 + cb + 4 * i + 1],
                                  acc[4 * i + 2] + cst[896 + cb + 4 * i + 2], acc[4 * i + 3] + cst[896 + cb + 4 * i + 3]);
           }
         }
@@ -544,10 +556,10 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
         float acc[32];
         tmem_ld32(tacc + cb, acc);
         tmem_wait_ld();
-        const float4* gw = reinterpret_cast<const float4*>(a.GW + (pt_ok ? pl : 0) * 128 + cb);
+        const uint8_t* gw = reinterpret_cast<const uint8_t*>(a.GW) + tile_f32_off(pt_ok ? pl : 0, cb >> 2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 q = __ldg(gw + i);
+          const float4 q = __ldg(reinterpret_cast<const float4*>(gw + i * 2048));
           acc[4 * i] = elu_fast(acc[4 * i] + q.x); acc[4 * i + 1] = elu_fast(acc[4 * i + 1] + q.y);
           acc[4 * i + 2] = elu_fast(acc[4 * i + 2] + q.z); acc[4 * i + 3] = elu_fast(acc[4 * i + 3] + q.w);
         }

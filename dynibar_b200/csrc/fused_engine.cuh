@@ -117,6 +117,14 @@ __host__ __device__ __forceinline__ size_t tile_image_bytes(long long rows, int 
   return (size_t)((rows + 127) >> 7) * (size_t)kgroups * 2048u;
 }
 
+// fp32 companion of the tile image for per-point vectors that stay fp32 (residual stream g2, the
+// blending head's per-point term GW): 128 columns in groups of 4 floats, element (row r, column c)
+// of a 128-row tile at byte  tile * 65536 + (c / 4) * 2048 + (r % 128) * 16 + (c % 4) * 4,
+// so that both the producer's and the consumer's per-row float4 accesses are warp-coalesced.
+__host__ __device__ __forceinline__ size_t tile_f32_off(long long row, int col4group) {
+  return (size_t)(row >> 7) * 65536u + (size_t)col4group * 2048u + (size_t)(row & 127) * 16u;
+}
+
 // The chunk table is staged into shared memory once per CTA: the producer and the issuer
 // read one entry per chunk on their critical path (a global load there costs an L2 round trip
 // per chunk and was the bottleneck of the MMA issue thread).

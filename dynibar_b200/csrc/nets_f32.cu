@@ -9,6 +9,7 @@
 #include "linear_tc.cuh"
 #include "nets.cuh"
 #include "nets_fused.cuh"
+#include "fused_engine.cuh"
 
 extern "C" long long* view_dbg_ptr();
 
@@ -328,10 +329,14 @@ __global__ void posenc_table_kernel(float* __restrict__ tab, int S) {
 // (mlp_network.py:23-24, :91-94).
 // ---------------------------------------------------------------------------
 // 4 consecutive elements of a [*,128] row stored as fp32 or bf16
+// BF: `base` is a bf16 tile image with 16 k-groups (fused_engine.cuh), elem = row * 128 + col
 template <bool BF>
 __device__ __forceinline__ float4 ld4(const void* base, long long elem) {
   if (BF) {
-    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem);
+    const long long row = elem >> 7;
+    const int col = (int)(elem & 127);
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(base) +
+                                                    fe::tile_image_off(row, col >> 3, 16) + (col & 7) * 2);
     const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
     const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
     return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
@@ -344,13 +349,16 @@ __device__ __forceinline__ void st4(void* base, long long elem, float4 v) {
     __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + elem) = u;
+    const long long row = elem >> 7;
+    const int col = (int)(elem & 127);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(base) + fe::tile_image_off(row, col >> 3, 16) +
+                              (col & 7) * 2) = u;
   } else {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem) = v;
   }
 }
 
-// BF: Q/K/V/O are bf16 rows (fused path) instead of fp32 (staged path)
+// BF: Q/K/V/O are bf16 tile images (fused path) instead of fp32 rows (staged path)
 template <bool BF>
 __global__ void attention_kernel(const void* __restrict__ Q, const void* __restrict__ K,
                                  const void* __restrict__ Vv, const float* __restrict__ nvalid, int S,
@@ -576,8 +584,10 @@ struct TrunkBufs {
 static void trunk_alloc(Bump& b, long long M, long long P, TrunkBufs* t) {
   t->H1 = b.f(M * 256); t->X = b.f(M * 128); t->H2 = b.f(M * 128); t->XV = b.f(M * 129);
   t->vis1 = b.f(M); t->vis2 = b.f(M); t->G = b.f(P * 257); t->nvalid = b.f(P);
-  t->GH = b.f(P * 256); t->G2 = b.f(P * 128); t->Q = b.f(P * 128); t->K = b.f(P * 128);
-  t->V = b.f(P * 128); t->O = b.f(P * 128); t->O2 = b.f(P * 128); t->G3 = b.f(P * 128);
+  // G2, Q, K, V, O double as the fused path's tile-layout buffers: whole 256-row iterations
+  const long long Pt = ((P + 255) / 256) * 256;
+  t->GH = b.f(P * 256); t->G2 = b.f(Pt * 128); t->Q = b.f(Pt * 128); t->K = b.f(Pt * 128);
+  t->V = b.f(Pt * 128); t->O = b.f(Pt * 128); t->O2 = b.f(P * 128); t->G3 = b.f(P * 128);
 }
 
 // per-point tail shared by the staged and the fused paths:
@@ -855,7 +865,7 @@ struct FusedBufs {
 static size_t fused_alloc(Bump& b, bool st_net, int R, int S, int V, FusedBufs* d) {
   const long long P = (long long)R * S, M = P * V;
   d->small = b.f(64);
-  d->G = b.f(P * kGStride);
+  d->G = b.f(((P + 255) / 256) * 256 * (kGStride / 2));  // bf16 tile image, 34 k-groups, whole iterations
   trunk_alloc(b, 0, P, &d->t);
   d->sh = b.f(P * 128); d->sig = b.f(P);
   if (st_net) {
@@ -865,7 +875,7 @@ static size_t fused_alloc(Bump& b, bool st_net, int R, int S, int V, FusedBufs* 
       d->X = b.f(slots * 64);
     }
     d->vis2 = b.f(M); d->rd = b.f(M * 4); d->meff = b.f(M); d->rgbin = b.f(M * 3);
-    d->ch = b.f(M * 128); d->ch2 = b.f(M * 64); d->logit = b.f(M);
+    d->ch = b.f((M > ((P + 255) / 256) * 256 ? M : ((P + 255) / 256) * 256) * 128); d->ch2 = b.f(M * 64); d->logit = b.f(M);
   } else {
     d->ptspe = b.f(P * 33); d->dirpe = b.f((long long)R * 27);
     d->G4h = b.f(P * 256); d->G4 = b.f(P * 128);
@@ -918,18 +928,64 @@ static int run_point_fused(const dyn_net* n, const float* G, long long P, int R,
 }
 
 // unit-test hook: the per-point fused stage on caller-provided G / nvalid
+// fp32 rows -> bf16 tile image with KG k-groups (columns >= ncols are zero)
+__global__ void rows_to_image_kernel(const float* __restrict__ src, int ld, int ncols, long long P, int KG,
+                                     uint8_t* __restrict__ img) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P * KG) return;
+  const long long row = e / KG;
+  const int kg = (int)(e % KG);
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (8 * kg + i < ncols) ? src[row * ld + 8 * kg + i] : 0.f;
+  *reinterpret_cast<uint4*>(img + fe::tile_image_off(row, kg, KG)) =
+      make_uint4(fe::pack_bf16x2(v[0], v[1]), fe::pack_bf16x2(v[2], v[3]), fe::pack_bf16x2(v[4], v[5]),
+                 fe::pack_bf16x2(v[6], v[7]));
+}
+// fp32 tile layout (tile_f32_off) -> fp32 rows [P,128]
+__global__ void tile_f32_to_rows_kernel(const uint8_t* __restrict__ src, long long P, float* __restrict__ dst) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P * 32) return;
+  const long long row = e >> 5;
+  const int cg = (int)(e & 31);
+  reinterpret_cast<float4*>(dst)[row * 32 + cg] = *reinterpret_cast<const float4*>(src + fe::tile_f32_off(row, cg));
+}
+
+// Unit-test hook: plain fp32 rows in and out; the tile layouts the fused kernels exchange are
+// converted here (scratch is allocated per call: this entry point is not on the product path).
+// The Q, K, V, O arguments are ignored (those intermediates live in tile-image scratch).
 int debug_point_chain(const dyn_net* n, const float* G, const float* nvalid, const float* pts,
                       const float* ray_dir, int R, int S, float* g2, float* Q, float* K, float* V,
                       float* O, float* out_a, float* out_b, float* posenc_ws, cudaStream_t st) {
+  (void)Q; (void)K; (void)V; (void)O;
+  const long long P = (long long)R * S;
+  if (P == 0) return DYN_OK;
+  const long long Pt = ((P + 255) / 256) * 256;
+  const size_t g_bytes = fe::tile_image_bytes(Pt, 34), t_bytes = (size_t)Pt * 512;
+  uint8_t* scratch = nullptr;
+  DYN_CUDA(cudaMalloc(&scratch, g_bytes + 6 * t_bytes));
+  DYN_CUDA(cudaMemsetAsync(scratch, 0, g_bytes + 6 * t_bytes, st));
+  uint8_t* gimg = scratch;
+  float* buf[6];
+  for (int i = 0; i < 6; ++i) buf[i] = reinterpret_cast<float*>(scratch + g_bytes + (size_t)i * t_bytes);
+  rows_to_image_kernel<<<cdiv(P * 34, 256), 256, 0, st>>>(G, kGStride, 257, P, 34, gimg);
   TrunkBufs t;
   memset(&t, 0, sizeof(t));
-  t.G2 = g2; t.Q = Q; t.K = K; t.V = V; t.O = O; t.nvalid = const_cast<float*>(nvalid);
+  t.G2 = buf[0]; t.Q = buf[1]; t.K = buf[2]; t.V = buf[3]; t.O = buf[4]; t.nvalid = const_cast<float*>(nvalid);
   Point2Args p2;
   memset(&p2, 0, sizeof(p2));
   const bool dynamic = n->kind == DYN_NET_DYNAMIC;
   if (dynamic) { p2.pts = pts; p2.ray_dir = ray_dir; p2.raw = out_a; }
-  else { p2.GW = out_a; p2.sigma = out_b; }
-  return run_point_fused(n, G, (long long)R * S, R, S, dynamic, posenc_ws, t, p2, st);
+  else { p2.GW = buf[5]; p2.sigma = out_b; }
+  int rc = run_point_fused(n, reinterpret_cast<const float*>(gimg), P, R, S, dynamic, posenc_ws, t, p2, st);
+  if (rc == DYN_OK) {
+    tile_f32_to_rows_kernel<<<cdiv(P * 32, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(buf[0]), P, g2);
+    if (!dynamic)
+      tile_f32_to_rows_kernel<<<cdiv(P * 32, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(buf[5]), P, out_a);
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(scratch);
+  return rc;
 }
 
 static int fill_view_args(ViewFusedArgs* a, const float* query_cam, const float* src_rgbs,

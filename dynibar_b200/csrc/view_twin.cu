@@ -525,15 +525,30 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           }
         }
         if (pt_ok && !(a.ablate & 4)) {
-          float* g = a.G + pl * kGStride;
+          // pooled statistics as the bf16 tile image of geometry_fc's operand (34 k-groups:
+          // mean 0..127 | var 128..255 | weight 256 | zero pad), rows = points
+          uint8_t* gi = reinterpret_cast<uint8_t*>(a.G);
+          float mu[NO], vr[NO];
 #pragma unroll
           for (int i = 0; i < NO; ++i) {
-            const float mu = mean[i];
-            g[cbase + i] = mu;
-            g[128 + cbase + i] = sq[i] - mu * mu * (2.f - W);
+            mu[i] = mean[i];
+            vr[i] = sq[i] - mu[i] * mu[i] * (2.f - W);
+          }
+          uint8_t* pm = gi + tile_image_off(pl, cbase >> 3, 34) + (cbase & 7) * 2;
+          uint8_t* pv = gi + tile_image_off(pl, 16 + (cbase >> 3), 34) + (cbase & 7) * 2;
+          if (NO == 8) {
+            *reinterpret_cast<uint4*>(pm) = make_uint4(pack_bf16x2(mu[0], mu[1]), pack_bf16x2(mu[2], mu[3]),
+                                                       pack_bf16x2(mu[4 % NO], mu[5 % NO]), pack_bf16x2(mu[6 % NO], mu[7 % NO]));
+            *reinterpret_cast<uint4*>(pv) = make_uint4(pack_bf16x2(vr[0], vr[1]), pack_bf16x2(vr[2], vr[3]),
+                                                       pack_bf16x2(vr[4 % NO], vr[5 % NO]), pack_bf16x2(vr[6 % NO], vr[7 % NO]));
+          } else {
+            *reinterpret_cast<uint2*>(pm) = make_uint2(pack_bf16x2(mu[0], mu[1]), pack_bf16x2(mu[2], mu[3]));
+            *reinterpret_cast<uint2*>(pv) = make_uint2(pack_bf16x2(vr[0], vr[1]), pack_bf16x2(vr[2], vr[3]));
           }
           if (gl == 0 && tw == 0) {
-            g[256] = W / (float)a.V;
+            *reinterpret_cast<uint4*>(gi + tile_image_off(pl, 32, 34)) =
+                make_uint4(pack_bf16x2(W / (float)a.V, 0.f), 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(gi + tile_image_off(pl, 33, 34)) = make_uint4(0u, 0u, 0u, 0u);
             a.nvalid[pl] = nval;
           }
         }
