@@ -145,16 +145,17 @@ __device__ __forceinline__ void stage_chunks(FusedChunk* s, const FusedChunk* __
 //   ping-pong (PP = true): per ROUND (chunks from a wait-flag to a last-flag) tile 0
 //     then tile 1, each with its own barriers (128 arrivals), so the MMA of one tile
 //     overlaps the epilogue of the other; weights stream twice.
-__device__ __forceinline__ uint32_t bar_aready(uint32_t bar0, int tile) { return bar0 + 8u * (8 + 2 * tile); }
-__device__ __forceinline__ uint32_t bar_acc(uint32_t bar0, int tile) { return bar0 + 8u * (9 + 2 * tile); }
+// generic layout for a ring of `ring` slots: [0,ring) w_full, [ring,2 ring) w_empty, then per tile a_ready, acc_full
+__device__ __forceinline__ uint32_t bar_aready(uint32_t bar0, int tile, int ring = kRing) { return bar0 + 8u * (2 * ring + 2 * tile); }
+__device__ __forceinline__ uint32_t bar_acc(uint32_t bar0, int tile, int ring = kRing) { return bar0 + 8u * (2 * ring + 1 + 2 * tile); }
 
 // `arrivals` = row threads per 128-row tile (128, or 256 in the twin-warp kernels)
-__device__ __forceinline__ void init_barriers(uint32_t bar0, bool pp, int arrivals = 128) {
-  for (int i = 0; i < kRing; ++i) { mbar_init(bar0 + 8u * i, 1); mbar_init(bar0 + 8u * (4 + i), 1); }
-  mbar_init(bar_aready(bar0, 0), pp ? arrivals : 2 * arrivals);
-  mbar_init(bar_acc(bar0, 0), 1);
-  mbar_init(bar_aready(bar0, 1), arrivals);
-  mbar_init(bar_acc(bar0, 1), 1);
+__device__ __forceinline__ void init_barriers(uint32_t bar0, bool pp, int arrivals = 128, int ring = kRing) {
+  for (int i = 0; i < ring; ++i) { mbar_init(bar0 + 8u * i, 1); mbar_init(bar0 + 8u * (ring + i), 1); }
+  mbar_init(bar_aready(bar0, 0, ring), pp ? arrivals : 2 * arrivals);
+  mbar_init(bar_acc(bar0, 0, ring), 1);
+  mbar_init(bar_aready(bar0, 1, ring), arrivals);
+  mbar_init(bar_acc(bar0, 1, ring), 1);
   mbar_fence_init();
 }
 
@@ -164,7 +165,7 @@ __device__ __forceinline__ int round_end(const FusedChunk* __restrict__ chunks, 
   return c + 1 < nchunks ? c + 1 : nchunks;
 }
 
-template <bool PP, int RING = kRing>
+template <bool PP, int RING = kRing, int STAGE = kStageBytes>
 __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chunks, int nchunks,
                                               const void* wimg, int n_iter, uint8_t* ring, uint32_t bar0) {
   const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(wimg);
@@ -175,10 +176,10 @@ __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chu
       for (int rep = 0; rep < (PP ? 2 : 1); ++rep) {
         for (int c = c0; c < c1; ++c, ++cnt) {
           const uint32_t st = cnt % RING;
-          if (cnt >= RING) mbar_wait(bar0 + 8u * (4 + st), ((cnt / RING) - 1) & 1);
+          if (cnt >= RING) mbar_wait(bar0 + 8u * (RING + st), ((cnt / RING) - 1) & 1);
           const FusedChunk ch = chunks[c];
           mbar_arrive_expect_tx(bar0 + 8u * st, ch.bytes);
-          bulk_g2s(smem_u32(ring + st * kStageBytes), wsrc + ch.off, ch.bytes, bar0 + 8u * st);
+          bulk_g2s(smem_u32(ring + st * STAGE), wsrc + ch.off, ch.bytes, bar0 + 8u * st);
         }
       }
       c0 = c1;
@@ -191,40 +192,40 @@ __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chu
 // round (commit acc_full), 8 = first k-step overwrites D (start of a layer);
 // d_col = accumulator column offset inside the tile's 256-column TMEM region.
 // NT = 128-row tiles per CTA (1 or 2), RING = weight-ring slots in use.
-template <bool PP, int NT = 2, int RING = kRing>
+template <bool PP, int NT = 2, int RING = kRing, int STAGE = kStageBytes>
 __device__ __forceinline__ void issuer_loop(const FusedChunk* __restrict__ chunks, int nchunks, int n_iter,
                                             uint8_t* smem, uint8_t* ring, uint32_t bar0,
                                             uint32_t tmem_base, int a_tile_bytes = kATileBytes,
                                             long long* dbg = nullptr) {
-  uint32_t cnt = 0, a_cnt[2] = {0, 0};
-  long long t_a = 0, t_w = 0, t_begin = clock64();
-  const uint32_t a_addr[2] = {smem_u32(smem), smem_u32(smem + a_tile_bytes)};
-  for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
-    for (int c0 = 0; c0 < nchunks;) {
-      const int c1 = PP ? round_end(chunks, c0, nchunks) : nchunks;
-      for (int rep = 0; rep < (PP ? 2 : 1); ++rep) {
-        for (int c = c0; c < c1; ++c, ++cnt) {
-          const FusedChunk ch = chunks[c];
-          long long t0 = dbg ? clock64() : 0;
-          if (ch.flags & 1) {
-            mbar_wait(bar_aready(bar0, PP ? rep : 0), a_cnt[PP ? rep : 0] & 1);
-            ++a_cnt[PP ? rep : 0];
+  // Entered by the whole (converged) warp; ONE elected lane then runs the loop alone, so every
+  // address / descriptor stays in uniform registers and no per-chunk warp re-convergence is needed.
+  if (elect_one()) {
+    uint32_t cnt = 0, a_cnt[2] = {0, 0};
+    long long t_a = 0, t_w = 0, t_begin = clock64();
+    const uint32_t a_addr[2] = {smem_u32(smem), smem_u32(smem + a_tile_bytes)};
+    for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
+      for (int c0 = 0; c0 < nchunks;) {
+        const int c1 = PP ? round_end(chunks, c0, nchunks) : nchunks;
+        for (int rep = 0; rep < (PP ? 2 : 1); ++rep) {
+          for (int c = c0; c < c1; ++c, ++cnt) {
+            const FusedChunk ch = chunks[c];
+            long long t0 = dbg ? clock64() : 0;
+            if (ch.flags & 1) {
+              mbar_wait(bar_aready(bar0, PP ? rep : 0, RING), a_cnt[PP ? rep : 0] & 1);
+              ++a_cnt[PP ? rep : 0];
+            }
+            long long t1 = dbg ? clock64() : 0;
+            const uint32_t st = cnt % RING;
+            mbar_wait(bar0 + 8u * st, (cnt / RING) & 1);
             tc_fence_after_sync();
-          }
-          long long t1 = dbg ? clock64() : 0;
-          const uint32_t st = cnt % RING;
-          mbar_wait(bar0 + 8u * st, (cnt / RING) & 1);
-          tc_fence_after_sync();
-          long long t2 = 0;
-          if (dbg) {
-            t2 = clock64();
-            t_a += t1 - t0;
-            t_w += t2 - t1;
-          }
-          // the whole warp runs the loop (warp-uniform values); one elected lane issues
-          if (elect_one()) {
+            long long t2 = 0;
+            if (dbg) {
+              t2 = clock64();
+              t_a += t1 - t0;
+              t_w += t2 - t1;
+            }
             const uint32_t idesc = idesc_bf16_f32(128, ch.npad);
-            const uint32_t w_addr = smem_u32(ring + st * kStageBytes);
+            const uint32_t w_addr = smem_u32(ring + st * STAGE);
             const uint32_t lbo_b = (uint32_t)ch.npad * 16u;
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
@@ -236,24 +237,24 @@ __device__ __forceinline__ void issuer_loop(const FusedChunk* __restrict__ chunk
                             ((ch.flags & 8) && ks == 0) ? 0u : 1u);
               }
             }
-            mma_commit(bar0 + 8u * (4 + st));
-            if (ch.flags & 2) mma_commit(bar_acc(bar0, PP ? rep : 0));
-          }
-          __syncwarp();
-          if (dbg && blockIdx.x == 0 && cnt < 120 && (threadIdx.x & 31) == 0) {
-            dbg[8 + 4 * cnt + 0] = t0; dbg[8 + 4 * cnt + 1] = t1;
-            dbg[8 + 4 * cnt + 2] = t2; dbg[8 + 4 * cnt + 3] = clock64();
+            mma_commit(bar0 + 8u * (RING + st));
+            if (ch.flags & 2) mma_commit(bar_acc(bar0, PP ? rep : 0, RING));
+            if (dbg && blockIdx.x == 0 && cnt < 120) {
+              dbg[8 + 4 * cnt + 0] = t0; dbg[8 + 4 * cnt + 1] = t1;
+              dbg[8 + 4 * cnt + 2] = t2; dbg[8 + 4 * cnt + 3] = clock64();
+            }
           }
         }
+        c0 = c1;
       }
-      c0 = c1;
+    }
+    if (dbg != nullptr && blockIdx.x == 0) {
+      dbg[0] = clock64() - t_begin;  // issuer lifetime
+      dbg[1] = t_a;                  // waiting for A operands (epilogues)
+      dbg[2] = t_w;                  // waiting for weight chunks (ring)
     }
   }
-  if (dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
-    dbg[0] = clock64() - t_begin;  // issuer lifetime
-    dbg[1] = t_a;                  // waiting for A operands (epilogues)
-    dbg[2] = t_w;                  // waiting for weight chunks (ring)
-  }
+  __syncwarp();
 }
 
 // ---- host side: weight images + chunk table ------------------------------------
@@ -273,8 +274,9 @@ struct HostLayer {
 };
 
 inline void append_layer(const HostLayer& L, std::vector<uint8_t>& img, std::vector<FusedChunk>& tab,
-                         int d_col = 0, int a_kgroup0 = 0, int first_flags = 9, bool last = true) {
-  int steps_per_chunk = kStageBytes / (L.Npad * 32);
+                         int d_col = 0, int a_kgroup0 = 0, int first_flags = 9, bool last = true,
+                         int stage_bytes = kStageBytes) {
+  int steps_per_chunk = stage_bytes / (L.Npad * 32);
   if (steps_per_chunk > 8) steps_per_chunk = 8;
   const int ksteps_total = L.Kpad / 16;
   for (int k0 = 0; k0 < ksteps_total; k0 += steps_per_chunk) {

@@ -32,8 +32,11 @@ constexpr int kTwinConst = T_XCH + 1024;
 // NT = 128-row tiles per CTA: 2 -> one 576-thread CTA per SM (ping-pong between its tiles);
 // 1 -> two independent 320-thread CTAs per SM, each with one tile and a 2-slot weight ring, so
 // the tensor pipe is shared by two unsynchronised instruction streams.
-constexpr int twin_ring(int nt) { return nt == 1 ? 2 : kRing; }
-constexpr int twin_smem(int nt) { return nt * kTwinATile + twin_ring(nt) * kStageBytes + kTwinConst * 4 + 256; }
+// weight ring: 16 KB stages; 8 KB stages x twice the slots measured 14 % slower (per-chunk barrier and
+// issue overhead outweighs the faster slot turnover, profiles/r01_kernels.md)
+constexpr int kTwinStage = 16384;
+constexpr int twin_ring(int nt) { return nt == 1 ? 2 : 4; }
+constexpr int twin_smem(int nt) { return nt * kTwinATile + twin_ring(nt) * kTwinStage + kTwinConst * 4 + 256; }
 
 __device__ __forceinline__ void pair_sync(int pair) {
   asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
@@ -76,15 +79,15 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
   constexpr int W_ISSUE = 8 * NT, W_PROD = 8 * NT + 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem + NT * kTwinATile;
-  float* cst = reinterpret_cast<float*>(ring + RING * kStageBytes);
+  float* cst = reinterpret_cast<float*>(ring + RING * kTwinStage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(cst + kTwinConst);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
   __shared__ __align__(16) FusedChunk s_tab[kMaxChunks];
   stage_chunks(s_tab, a.chunks, a.nchunks);
 
-  if (tid == 0) init_barriers(bar0, PP, /*arrivals=*/NT == 2 ? 256 : 128);
+  if (tid == 0) init_barriers(bar0, PP, /*arrivals=*/NT == 2 ? 256 : 128, RING);
   {
     const float* prm = a.params;
     for (int i = tid; i < 256; i += blockDim.x) {
@@ -117,9 +120,9 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
   const int n_iter = (int)((n_rows + ROWS - 1) / ROWS);
 
   if (warp == W_PROD) {
-    if ((tid & 31) == 0) producer_loop<PP, RING>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) == 0) producer_loop<PP, RING, kTwinStage>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == W_ISSUE) {
-    issuer_loop<PP, NT, RING>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kTwinATile,
+    issuer_loop<PP, NT, RING, kTwinStage>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kTwinATile,
                            a.dbg ? a.dbg + 128 : nullptr);
   } else {
     const int tw = tid / ROWS;         // twin index
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         for (int g = 0; g < 7; ++g) store8(arow, 56 * tw + 8 * g, xin + 8 * g);
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(bar_aready(bar0, bt));
+        mbar_arrive(bar_aready(bar0, bt, RING));
       }
 
       TS();  // 1: after F1 operand + arrive
@@ -289,16 +292,16 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       TS();  // 2: after gather
       if (ST) {
         // ---- F1 epilogue: this twin's 128 of the 256 columns ----
-        mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+        mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
         TS();  // 3: F1 acc ready
         tc_fence_after_sync();
         elu_block_to_A<128>(arow, tacc, 128 * tw, cst + T_B1);
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(bar_aready(bar0, bt));
+        mbar_arrive(bar_aready(bar0, bt, RING));
         TS();  // 4: F1 epilogue done
         // ---- F2: src_feat (35 of 48 columns) * ref_feat; twin 0 keeps 0..17, twin 1 keeps 18..34 ----
-        mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+        mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
         TS();  // 5: F2 acc ready
         tc_fence_after_sync();
         float s48[48];
@@ -363,22 +366,22 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, bt));
+      mbar_arrive(bar_aready(bar0, bt, RING));
 
       TS();  // 6: pool1 done + arrive
       // ---- F3: ELU(base_fc.0), this twin's 128 columns ----
-      mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
       TS();  // 7: F3 acc ready
       tc_fence_after_sync();
       elu_block_to_A<128>(arow, tacc, 128 * tw, cst + T_B3);
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, bt));
+      mbar_arrive(bar_aready(bar0, bt, RING));
 
       const int c0 = 64 * tw;  // this twin's columns of the 128-wide layers
       TS();  // 8: F3 epilogue done
       // ---- F4: x = ELU(base_fc.2) -> TMEM [128,256); A = x * w1 ----
-      mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
       TS();  // 9: F4 acc ready
       tc_fence_after_sync();
 #pragma unroll 1
@@ -397,11 +400,11 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, bt));
+      mbar_arrive(bar_aready(bar0, bt, RING));
 
       TS();  // 10: F4 epilogue done
       // ---- F5: h = ELU(vis_fc.0) -> A; partial visibility logit ----
-      mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
       TS();  // 11: F5 acc ready
       tc_fence_after_sync();
       {
@@ -423,11 +426,11 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, bt));
+      mbar_arrive(bar_aready(bar0, bt, RING));
 
       TS();  // 12: F5 epilogue done
       // ---- F6: x += ELU(vis_fc.2[:128]); A = x * vis1 ----
-      mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
       TS();  // 13: F6 acc ready
       tc_fence_after_sync();
       // both twins arrived on a_ready before this MMA ran: the partial logits are visible
@@ -460,11 +463,11 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, bt));
+      mbar_arrive(bar_aready(bar0, bt, RING));
 
       TS();  // 14: F6 epilogue done
       // ---- F7: vis2 = sigmoid(vis_fc2.2 . ELU(vis_fc2.0)) * mask ----
-      mbar_wait(bar_acc(bar0, bt), acc_cnt & 1); ++acc_cnt;
+      mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
       TS();  // 15: F7 acc ready
       tc_fence_after_sync();
       {
@@ -578,7 +581,7 @@ int view_twin_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes,
   auto add = [&](const LinearP& l, int N, int Npad, int Kpad, std::vector<int> map) {
     HostLayer L;
     L.W = P + l.w; L.N = N; L.Kw = l.in; L.Npad = Npad; L.Kpad = Kpad; L.colmap = std::move(map);
-    append_layer(L, img, tab);
+    append_layer(L, img, tab, 0, 0, 9, true, kTwinStage);
   };
   if (n->kind == DYN_NET_STATIC) {
     const StaticLayout& L = n->sl;

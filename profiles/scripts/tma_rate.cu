@@ -1,0 +1,56 @@
+// Micro-benchmark: sustained cp.async.bulk (global/L2 -> shared) rate per SM as a function of the
+// number of 16 KB copies in flight and of the CTAs per SM, all SMs streaming the same 384 KB
+// L2-resident buffer (the weight-streaming pattern of the fused kernels).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I dynibar_b200/csrc -o profiles/scripts/tma_rate profiles/scripts/tma_rate.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "tc.cuh"
+using namespace dyn::tc;
+
+__global__ void __launch_bounds__(64) rate_kernel(const uint8_t* src, int src_chunks, int slots, int chunk_bytes,
+                                                  int n_copies, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[16];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < slots; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long t0 = clock64();
+    for (int c = 0; c < n_copies + slots; ++c) {
+      const int s = c % slots;
+      if (c >= slots) mbar_wait(smem_u32(&bars[s]), ((c / slots) - 1) & 1);  // copy c - slots has landed
+      if (c < n_copies) {
+        mbar_arrive_expect_tx(smem_u32(&bars[s]), chunk_bytes);
+        bulk_g2s(smem_u32(smem + (size_t)s * chunk_bytes), src + (size_t)((c + blockIdx.x) % src_chunks) * chunk_bytes,
+                 chunk_bytes, smem_u32(&bars[s]));
+      }
+    }
+    out[blockIdx.x] = clock64() - t0;
+  }
+}
+
+int main() {
+  const int chunk = 16384, src_chunks = 24;
+  uint8_t* src; cudaMalloc(&src, (size_t)chunk * src_chunks); cudaMemset(src, 1, (size_t)chunk * src_chunks);
+  long long* out; cudaMalloc(&out, sizeof(long long) * 296);
+  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * chunk);
+  const int n = 400;
+  for (int cps : {1, 2}) {
+    for (int slots : {1, 2, 3, 4, 6, 8}) {
+      if (cps == 2 && slots > 6) continue;
+      const int grid = 148 * cps;
+      const int smem = cps == 2 ? 6 * chunk : 8 * chunk;  // pins the CTAs-per-SM count
+      for (int rep = 0; rep < 2; ++rep) rate_kernel<<<grid, 64, smem>>>(src, src_chunks, slots, chunk, n, out);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long h[296]; cudaMemcpy(h, out, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+      double s = 0; for (int i = 0; i < grid; ++i) s += h[i];
+      const double cyc = s / grid;
+      printf("CTAs/SM %d  copies in flight/CTA %d  : %6.1f B/clk per CTA, %6.1f B/clk per SM, %6.0f cycles per 16 KB copy round trip  %s\n",
+             cps, slots, (double)n * chunk / cyc, (double)n * chunk / cyc * cps, cyc / n * slots, cudaGetErrorString(e));
+    }
+  }
+  return 0;
+}
