@@ -29,6 +29,12 @@ __device__ __forceinline__ float elu_fast(float x) {
   float e = ex2f(x * 1.4426950408889634f);
   return x > 0.f ? x : e - 1.f;
 }
+// ELU on the exp2 scale: x2 = log2(e) * x in, log2(e) * ELU(x) out (4 instructions; the producing layer's
+// weights and folded bias carry the log2 e, the consuming layer's weights the ln 2)
+__device__ __forceinline__ float elu_log2(float x2) {
+  const float e = ex2f(x2);
+  return x2 > 0.f ? x2 : fmaf(e, 1.4426950408889634f, -1.4426950408889634f);
+}
 __device__ __forceinline__ float sigmoid_fast(float x) {
   return __frcp_rn(1.f + ex2f(-x * 1.4426950408889634f));
 }
@@ -270,8 +276,20 @@ inline uint16_t f2bf(float f) {
 struct HostLayer {
   const float* W;  // host fp32 [*, Kw]
   int N, Kw, Npad, Kpad;
-  std::vector<int> colmap;  // size Kpad: weight column or -1
+  std::vector<int> colmap;  // size Kpad: weight column, -1 (zero), or kBiasHi / kBiasLo
+  // bias folded into the MMA: the operand carries 1.0 in the kBiasHi and kBiasLo columns and the image
+  // holds bf16(b) and bf16(b - bf16(b)) there (error 2^-17 |b|); `scale` multiplies weights and bias
+  // (log2 e for layers whose ELU is evaluated on the exp2 scale, ln 2 for their consumers)
+  const float* bias = nullptr;
+  float scale = 1.f;
 };
+constexpr int kBiasHi = -2, kBiasLo = -3;
+inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
 
 inline void append_layer(const HostLayer& L, std::vector<uint8_t>& img, std::vector<FusedChunk>& tab,
                          int d_col = 0, int a_kgroup0 = 0, int first_flags = 9, bool last = true,
@@ -294,7 +312,15 @@ inline void append_layer(const HostLayer& L, std::vector<uint8_t>& img, std::vec
     for (int n = 0; n < L.Npad; ++n)
       for (int kk = 0; kk < ks * 16; ++kk) {
         const int col = L.colmap[k0 * 16 + kk];
-        const float val = (n < L.N && col >= 0) ? L.W[(size_t)n * L.Kw + col] : 0.f;
+        float val = 0.f;
+        if (n < L.N) {
+          if (col >= 0) {
+            val = L.W[(size_t)n * L.Kw + col] * L.scale;
+          } else if (L.bias != nullptr && (col == kBiasHi || col == kBiasLo)) {
+            const float b = L.bias[n] * L.scale, hi = bf2f(f2bf(b));
+            val = col == kBiasHi ? hi : b - hi;
+          }
+        }
         dst[tile_off((uint32_t)L.Npad, (uint32_t)n, (uint32_t)kk) / 2] = f2bf(val);
       }
     tab.push_back(ch);

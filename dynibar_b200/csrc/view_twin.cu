@@ -56,6 +56,21 @@ __device__ __forceinline__ void pe_comp(float x, float* o) {
   }
 }
 
+// layers whose bias rides in the MMA and whose accumulator is on the exp2 scale (F1, F3)
+template <int N>
+__device__ __forceinline__ void elu_log2_block_to_A(uint8_t* arow, uint32_t tacc, int col0) {
+#pragma unroll 1
+  for (int cb = 0; cb < N; cb += 32) {
+    float acc[32];
+    tmem_ld32(tacc + col0 + cb, acc);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = elu_log2(acc[i]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) store8(arow, col0 + cb + 8 * g, acc + 8 * g);
+  }
+}
+
 template <int N>
 __device__ __forceinline__ void elu_block_to_A(uint8_t* arow, uint32_t tacc, int col0, const float* bias) {
 #pragma unroll 1
@@ -202,8 +217,9 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           pe_comp(pl6[2], xin); pe_comp(pl6[3], xin + 11); pe_comp(pl6[4], xin + 22);
           pe_comp(pl6[5], xin + 33);
           xin[44] = rd[0]; xin[45] = rd[1]; xin[46] = rd[2]; xin[47] = rd[3];
+          xin[48] = 1.f; xin[49] = 1.f;  // bias columns of ray_dir_fc.0 (hi, lo)
 #pragma unroll
-          for (int i = 48; i < 56; ++i) xin[i] = 0.f;
+          for (int i = 50; i < 56; ++i) xin[i] = 0.f;
         }
         if (!valid) {
 #pragma unroll
@@ -295,7 +311,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
         TS();  // 3: F1 acc ready
         tc_fence_after_sync();
-        elu_block_to_A<128>(arow, tacc, 128 * tw, cst + T_B1);
+        elu_log2_block_to_A<128>(arow, tacc, 128 * tw);
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(bar_aready(bar0, bt, RING));
@@ -355,6 +371,8 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
             const float s2 = group_sum<VP>(w1 * d * d);
             o[j] = s1; o[8 + j] = s2; o[16 + j] = fv;
           }
+          // bias columns of base_fc.0 (hi, lo): the last (unused) channel slot of twin 0
+          if (tw == 0 && g == ng0 - 1) { o[7] = 1.f; o[15] = 1.f; }
           store8(arow, col_base + 24 * g, o);
           store8(arow, col_base + 24 * g + 8, o + 8);
           store8(arow, col_base + 24 * g + 16, o + 16);
@@ -373,7 +391,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
       TS();  // 7: F3 acc ready
       tc_fence_after_sync();
-      elu_block_to_A<128>(arow, tacc, 128 * tw, cst + T_B3);
+      elu_log2_block_to_A<128>(arow, tacc, 128 * tw);
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(bar_aready(bar0, bt, RING));
@@ -578,9 +596,14 @@ size_t view_twin_bytes(int kind) { (void)kind; return (size_t)(512 * 1024); }
 int view_twin_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes, cudaStream_t st) {
   std::vector<uint8_t> img;
   std::vector<FusedChunk> tab;
-  auto add = [&](const LinearP& l, int N, int Npad, int Kpad, std::vector<int> map) {
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  // fold_bias: the layer's bias rides in the map's kBiasHi / kBiasLo columns
+  auto add = [&](const LinearP& l, int N, int Npad, int Kpad, std::vector<int> map, float scale = 1.f,
+                 bool fold_bias = false) {
     HostLayer L;
     L.W = P + l.w; L.N = N; L.Kw = l.in; L.Npad = Npad; L.Kpad = Kpad; L.colmap = std::move(map);
+    L.scale = scale;
+    if (fold_bias) L.bias = P + l.b;
     append_layer(L, img, tab, 0, 0, 9, true, kTwinStage);
   };
   if (n->kind == DYN_NET_STATIC) {
@@ -597,8 +620,9 @@ int view_twin_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes,
     for (int ci = 5; ci < 9; ++ci)
       for (int j = 0; j < 11; ++j) m1[56 + 11 * (ci - 5) + j] = comp_col(ci, j);
     for (int i = 0; i < 4; ++i) m1[100 + i] = 99 + i;
-    add(L.ray_dir0, 256, 256, 112, m1);
-    add(L.ray_dir2, kF, 48, 256, identity_map(256, 256));
+    m1[104] = kBiasHi; m1[105] = kBiasLo;
+    add(L.ray_dir0, 256, 256, 112, m1, kLog2e, true);               // ELU on the exp2 scale
+    add(L.ray_dir2, kF, 48, 256, identity_map(256, 256), kLn2);     // consumes log2(e) * ELU
     // layer 3: per twin 5 groups of [mean8 | var8 | feat8]; concat channel c: mean c, var 70+c, feat 140+c
     std::vector<int> m3(240, -1);
     auto chan = [](int tw, int slot) {  // concat channel (0..69) of a twin's slot, -1 = pad
@@ -612,8 +636,9 @@ int view_twin_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes,
         const int base = 120 * tw + 24 * (s / 8) + (s % 8);
         m3[base] = c; m3[base + 8] = 70 + c; m3[base + 16] = 140 + c;
       }
-    add(L.base0, 256, 256, 240, m3);
-    add(L.base2, 128, 128, 256, identity_map(256, 256));
+    m3[103] = kBiasHi; m3[111] = kBiasLo;  // twin 0, slot 39 (unused): mean / var columns of group 4
+    add(L.base0, 256, 256, 240, m3, kLog2e, true);
+    add(L.base2, 128, 128, 256, identity_map(256, 256), kLn2);
     add(L.vis0, 128, 128, 128, identity_map(128, 128));
     add(L.vis2, 128, 128, 128, identity_map(128, 128));
     add(L.vis2_0, 128, 128, 128, identity_map(128, 128));
@@ -627,8 +652,9 @@ int view_twin_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes,
       const int c = 19 + s, b = 72 + 24 * (s / 8) + (s % 8);
       m3[b] = c; m3[b + 8] = 35 + c; m3[b + 16] = 70 + c;
     }
-    add(L.base0, 256, 256, 128, m3);
-    add(L.base2, 128, 128, 256, identity_map(256, 256));
+    m3[55] = kBiasHi; m3[63] = kBiasLo;  // twin 0, slot 23 (unused): mean / var columns of group 2
+    add(L.base0, 256, 256, 128, m3, kLog2e, true);
+    add(L.base2, 128, 128, 256, identity_map(256, 256), kLn2);
     add(L.vis0, 128, 128, 128, identity_map(128, 128));
     add(L.vis2, 128, 128, 128, identity_map(128, 128));
     add(L.vis2_0, 128, 128, 128, identity_map(128, 128));
