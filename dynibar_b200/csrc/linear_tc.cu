@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const __grid_constant
   const uint32_t w_chunk_bytes = (uint32_t)a.Npad * kKC * 2;
 
   if (warp == 8) {
-    if ((tid & 31) == 0) {
+    // the whole warp arrives converged; one ELECTED lane runs the loop (uniform-register descriptors,
+    // see fused_engine.cuh: issuer_loop)
+    if (elect_one()) {
       // ---------------- weight producer + MMA issuer ----------------
       const uint32_t idesc = idesc_bf16_f32(128, a.Npad);
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.Wp);

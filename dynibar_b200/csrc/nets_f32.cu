@@ -892,7 +892,8 @@ size_t net_fused_workspace(int kind, int R, int S, int V) {
 }
 
 // per-point stage on the fused chains: point1 (geometry_fc, Q|K|V) -> ray-transformer
-// attention (SIMT fp32) -> point2 (fc + LayerNorm + heads)
+// attention (tcgen05 when S divides 128, else the SIMT kernel) -> point2 (fc + LayerNorm + heads);
+// G, Q, K, V, O are bf16 tile images, g2 / GW use the fp32 tile layout (fused_engine.cuh)
 static int run_point_fused(const dyn_net* n, const float* G, long long P, int R, int S, bool dynamic,
                            float* posenc_tab, TrunkBufs& t, Point2Args& p2, cudaStream_t st) {
   Point1Args p1;

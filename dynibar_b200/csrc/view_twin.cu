@@ -1,17 +1,27 @@
-// Twin-warp version of the fused per-(point, view) stage (see nets_fused.cu for the
-// single-warp-per-row version and the math; reference: ibrnet/projection.py:103-176,
-// ibrnet/mlp_network.py:236-284 / :423-497).
+// Fused per-(point, view) stage of the two aggregation networks on tcgen05 (reference:
+// ibrnet/projection.py:103-176, ibrnet/mlp_network.py:236-284 (dynamic) / :423-497 (static)).
+// Per 128-row tile, without leaving the SM:
 //
-// Same engine (persistent CTA, two 128-row UMMA tiles, ping-pong MMA schedule,
-// weight ring), but every row is served by TWO threads in twin warps w and w+8
-// (same TMEM lane quadrant): 16 row warps per SM instead of 8, which is what the
-// latency-bound epilogues need.  Each twin owns half of every layer's output
-// columns and half of the gathered / pooled channels; the twins exchange only two
-// scalars per row and iteration (the partial visibility logits).
+//   projection + in-front/in-bounds masks + view-angle difference   (a4, a6)
+//   bilinear gather of source RGB + features from L2-resident maps  (a5)
+//   [static]  Plucker coords, positional encodings, ray_dir_fc     (a7, a8, a10)
+//   pooling weights, weighted mean/var over views (warp shuffles)  (a9/a10)
+//   base_fc -> vis_fc -> vis_fc2 (tensor cores, fp32 accum in TMEM)
+//   visibility re-weighting and the second mean/var pooling -> G (bf16 tile image) per point
 //
-//   warps 0-7  : twin 0 of rows (tile = w >> 2, quadrant = w & 3)
-//   warps 8-15 : twin 1 of the same rows
-//   warp 16    : MMA issuer        warp 17 : weight producer
+// Engine: fused_engine.cuh (operand tile in shared memory written by the epilogues, accumulators
+// in TMEM, weights streamed through a cp.async.bulk ring, table-driven MMA issuer).  Every row is
+// served by TWO threads in twin warps w and w + 4*NT (same TMEM lane quadrant), which is what the
+// latency-bound epilogues need; each twin owns half of every layer's output columns and half of the
+// gathered / pooled channels, and the twins exchange only two scalars per row and iteration (the
+// partial visibility logits).
+//
+// Default NT = 1: TWO independent CTAs per SM, each with one 128-row tile:
+//   warps 0-3 : twin 0 (quadrant = w & 3)      warps 4-7 : twin 1 of the same rows
+//   warp 8    : MMA issuer (one elected lane)  warp 9    : weight producer
+// NT = 2 (DYN_VIEW_TILES=2, kept for comparison): one 576-thread CTA per SM with two tiles in a
+// ping-pong schedule (warps 0-7 / 8-15 twins, 16 issuer, 17 producer); measured 5 % slower because the
+// two tiles run in lock step behind the in-order issuer (profiles/r01_kernels.md).
 #include <cstdlib>
 #include "fused_engine.cuh"
 #include "geometry.cuh"
