@@ -22,14 +22,19 @@ namespace {
 constexpr int kTile = 128 * 128 * 2;  // one bf16 [128 x 128] canonical tile: 32 KB
 constexpr int kQSlice = 128 * 32 * 2;  // Q_h: [128 x 32] = 8 KB
 // K, V, P tiles + Q_h slice + barriers/inv: 104 KB + 2.3 KB -> two CTAs per SM
-constexpr int kSmemAttn = 3 * kTile + kQSlice + 256 + 128 * 4 * 4;
+// + barriers (256 B) + per-row partial softmax sums [2 twins][128][4 heads] + partial maxima [2][128]
+constexpr int kSmemAttn = 3 * kTile + kQSlice + 256 + 2 * 128 * 4 * 4 + 2 * 128 * 4;
 
 // idesc with B in MN-major layout (bit 16)
 __host__ __device__ constexpr uint32_t idesc_bf16_f32_bmn(int M, int N) {
   return idesc_bf16_f32(M, N) | (1u << 16);
 }
 
-__global__ void __launch_bounds__(128, 2)
+// TW: two threads per row in twin warps w, w+4 (same TMEM lane quadrant): each twin owns half of the
+// row's keys in the softmax and half of every head's output dims (needs S % 64 == 0 so that a twin's
+// key range is whole 32-column TMEM blocks).  16 row warps per SM instead of 8.
+template <bool TW>
+__global__ void __launch_bounds__(TW ? 256 : 128, 2)
 attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K,
                     const __nv_bfloat16* __restrict__ V, const float* __restrict__ nvalid, long long P, int S,
                     __nv_bfloat16* __restrict__ O) {
@@ -52,15 +57,20 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)(warp * 32), 0);
+  const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), 0);
 
-  const int r = tid;
+  const int r = tid & 127, tw = tid >> 7;
+  const int rw = warp & 3;  // row warp: rows 32 rw .. 32 rw + 31
   const size_t roff = (size_t)(r >> 3) * 128 + (r & 7) * 16;
   const int ray_lo = (r / S) * S;  // first key row (inside the tile) of this row's ray
-  // key range touched by ANY row of this warp (tcgen05.ld is warp-collective: the
-  // column blocks a warp skips must be the same for all its lanes)
-  const int warp_lo = ((warp * 32) / S) * S;
-  const int warp_hi = ((warp * 32 + 31) / S + 1) * S;
+  // this THREAD's keys [k_lo, k_hi) and the key range touched by ANY row of this warp (tcgen05.ld is
+  // warp-collective: the column blocks a warp skips must be the same for all its lanes)
+  const int k_lo = TW ? ray_lo + tw * (S >> 1) : ray_lo;
+  const int k_hi = TW ? k_lo + (S >> 1) : ray_lo + S;
+  const int warp_lo = TW ? k_lo : ((rw * 32) / S) * S;
+  const int warp_hi = TW ? k_hi : ((rw * 32 + 31) / S + 1) * S;
+  float* den_part = reinterpret_cast<float*>(bars + 8);        // [2][128][4]
+  float* max_part = den_part + 2 * 128 * 4;                    // [2][128]
   const float scale = 0.17677669529663687f;  // 1 / sqrt(32)
   uint32_t ph_s = 0, ph_o = 0, ph_kv = 0, ph_q = 0;
   const uint8_t* qimg = reinterpret_cast<const uint8_t*>(Q);
@@ -116,8 +126,13 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int key = cb + i;
-          if (key >= ray_lo && key < ray_lo + S) mx = fmaxf(mx, q_valid ? l[i] * scale : 0.f);
+          if (key >= k_lo && key < k_hi) mx = fmaxf(mx, q_valid ? l[i] * scale : 0.f);
         }
+      }
+      if (TW) {  // combine the twins' maxima
+        max_part[tw * 128 + r] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + rw) : "memory");
+        mx = fmaxf(mx, max_part[(tw ^ 1) * 128 + r]);
       }
       float den = 0.f;
       // previous head's P V must be done before P is overwritten
@@ -126,6 +141,9 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
       for (int cb = 0; cb < 128; cb += 32) {
         float p[32];
         const bool any = !(cb + 32 <= warp_lo || cb >= warp_hi);
+        // twins: a block outside the warp's keys belongs to the other twin or to another ray; the
+        // latter (P must be zero there) are split between the twins by block parity
+        if (TW && !any && ((cb + 32 <= ray_lo || cb >= ray_lo + S) ? ((cb >> 5) & 1) != tw : true)) continue;
         if (any) {
           tmem_ld32(tacc + cb, p);
           tmem_wait_ld();
@@ -134,7 +152,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
         for (int i = 0; i < 32; ++i) {
           const int key = cb + i;
           float e = 0.f;
-          if (any && key >= ray_lo && key < ray_lo + S) e = q_valid ? __expf(p[i] * scale - mx) : 1.f;
+          if (any && key >= k_lo && key < k_hi) e = q_valid ? __expf(p[i] * scale - mx) : 1.f;
           p[i] = e;
           den += e;
         }
@@ -147,7 +165,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
           *reinterpret_cast<uint4*>(pt + roff + ((cb >> 3) + g) * 2048) = q;
         }
       }
-      reinterpret_cast<float*>(bars + 8)[r * 4 + h] = 1.f / den;  // applied when O is written out
+      den_part[(tw * 128 + r) * 4 + h] = den;  // 1 / sum applied when O is written out
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncthreads();  // P complete; every thread is done reading logits_h
@@ -171,17 +189,19 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
     mbar_wait(bar_o, ph_o & 1);
     ++ph_o;
     tc_fence_after_sync();
-    const float* invs = reinterpret_cast<const float*>(bars + 8) + r * 4;
+    constexpr int ND = TW ? 16 : 32;  // output dims of a head written by this thread
 #pragma unroll 1
     for (int h = 0; h < 4; ++h) {
-      float o[32];
-      tmem_ld32(tacc + 128 + 32 * h, o);
+      float o[ND];
+      if (TW) tmem_ld16(tacc + 128 + 32 * h + 16 * tw, o);
+      else tmem_ld32(tacc + 128 + 32 * h, o);
       tmem_wait_ld();
       if (ok) {
-        const float inv = invs[h];
-        uint8_t* dst = reinterpret_cast<uint8_t*>(O) + (size_t)tile * kTile + (size_t)(4 * h) * 2048 + (size_t)r * 16;
+        const float inv = 1.f / (den_part[r * 4 + h] + (TW ? den_part[(128 + r) * 4 + h] : 0.f));
+        uint8_t* dst = reinterpret_cast<uint8_t*>(O) + (size_t)tile * kTile +
+                       (size_t)(4 * h + (TW ? 2 * tw : 0)) * 2048 + (size_t)r * 16;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < ND / 8; ++i)
           *reinterpret_cast<uint4*>(dst + i * 2048) = make_uint4(pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv),
                               pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
                               pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv),
@@ -210,9 +230,14 @@ int launch_attention_tc(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __
   const long long n_tiles = (P + 127) / 128;
   const int grid = (int)(n_tiles < 2 * sms ? n_tiles : 2 * sms);
   const int smem = kSmemAttn;
-  DYN_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   ProfScope prof(PROF_ATTENTION, st);
-  attention_tc_kernel<<<grid, 128, smem, st>>>(Q, K, V, nvalid, P, S, O);
+  if (S % 64 == 0) {  // twin warps
+    DYN_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attention_tc_kernel<true><<<grid, 256, smem, st>>>(Q, K, V, nvalid, P, S, O);
+  } else {
+    DYN_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attention_tc_kernel<false><<<grid, 128, smem, st>>>(Q, K, V, nvalid, P, S, O);
+  }
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }
