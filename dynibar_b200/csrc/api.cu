@@ -246,6 +246,17 @@ int dyn_debug_point_chain(dyn_net_t net, const float* G, const float* nvalid, co
                            (cudaStream_t)stream);
 }
 
+int dyn_debug_pack_layer(const float* W, const float* bias, int N, int Kw, int Npad, int Kpad,
+                         const int* colmap, float scale, int stage_bytes, void* out_img, size_t out_bytes,
+                         size_t* img_bytes, int* nchunks) {
+  DYN_CHECK_ARG(W && colmap && out_img && img_bytes && nchunks);
+  return debug_pack_layer(W, bias, N, Kw, Npad, Kpad, colmap, scale, stage_bytes, out_img, out_bytes, img_bytes,
+                          nchunks);
+}
+size_t dyn_debug_tile_image_off(long long row, int kgroup, int kgroups) {
+  return debug_tile_image_off(row, kgroup, kgroups);
+}
+
 int dyn_motion_coeffs(dyn_net_t motion, const float* pts, float time, int R, int S, float* coeff,
                       void* workspace, size_t workspace_bytes, int precision, void* stream) {
   if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)

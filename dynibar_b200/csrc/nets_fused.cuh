@@ -113,6 +113,10 @@ struct RgbHeadArgs {
   int nchunks;
 };
 
+int debug_pack_layer(const float* W, const float* bias, int N, int Kw, int Npad, int Kpad, const int* colmap,
+                     float scale, int stage_bytes, void* out_img, size_t out_bytes, size_t* img_bytes,
+                     int* nchunks);
+size_t debug_tile_image_off(long long row, int kgroup, int kgroups);
 size_t fused_chain_bytes(int kind);
 int fused_chain_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes,
                       cudaStream_t st);

@@ -224,8 +224,9 @@ int dyn_flow_sceneflow(const float* weights, const float* pts_seq,
 
 /* ---- unit-test hook: the fused per-point stage (geometry_fc -> ray transformer
  * -> heads; mlp_network.py:283-315 / :496-506) on caller-provided pooled
- * features G [R*S, 272] (257 used) and nvalid [R*S].  Outputs the intermediates
- * g2, Q, K, V, O [R*S,128]; dynamic net: out_a = raw [R*S,4]; static net:
+ * features G [R*S, 272] (257 used) and nvalid [R*S].  Outputs g2 [R*S,128] (plain
+ * fp32 rows; the Q, K, V, O arguments are ignored: those intermediates live in
+ * the kernels' internal tile-image scratch); dynamic net: out_a = raw [R*S,4]; static net:
  * out_a = per-point part of rgb_fc.0 [R*S,128], out_b = masked sigma [R*S].
  * posenc_ws: S*128 floats of scratch. */
 int dyn_debug_point_chain(dyn_net_t net, const float* G, const float* nvalid,
@@ -233,6 +234,22 @@ int dyn_debug_point_chain(dyn_net_t net, const float* G, const float* nvalid,
                           float* g2, float* Q, float* K, float* V, float* O,
                           float* out_a, float* out_b, float* posenc_ws,
                           void* stream);
+
+/* ---- unit-test hook (HOST only, no GPU needed): pack one nn.Linear [N, Kw] into the bf16
+ * UMMA weight image the fused kernels stream (dynibar_b200/csrc/fused_engine.cuh:
+ * append_layer).  colmap[Kpad] maps operand column -> weight column, -1 = zero,
+ * -2 / -3 = hi / lo bf16 halves of the folded bias; `scale` multiplies weights and
+ * bias.  Chunks of `stage_bytes`; element (n, k) of a chunk that starts at k0 sits at
+ * byte ((k-k0)/8)*(Npad*16) + (n/8)*128 + (n%8)*16 + ((k-k0)%8)*2 of that chunk.
+ * Writes the image into out_img (out_bytes capacity), its size into *img_bytes and the
+ * number of chunks into *nchunks. */
+int dyn_debug_pack_layer(const float* W, const float* bias, int N, int Kw, int Npad,
+                         int Kpad, const int* colmap, float scale, int stage_bytes,
+                         void* out_img, size_t out_bytes, size_t* img_bytes,
+                         int* nchunks);
+/* byte offset of (row, 8-column group) in a bf16 tile image with `kgroups` groups per
+ * 128-row tile: the layout activations use between the fused kernels. */
+size_t dyn_debug_tile_image_off(long long row, int kgroup, int kgroups);
 
 /* profiling hook: when set, block 0 of the fused static per-view kernel writes clock64()
  * phase timestamps ([2 twins][64]) into dev_buf (profiles/scripts/prof_phases.py). */
