@@ -236,6 +236,19 @@ def test_wide_view_counts_use_16_slot_kernels():
   assert torch.equal(got["mask"], ref["mask"])
 
 
+def test_config4_sample_counts_use_simt_attention_for_192_samples():
+  """BASELINE config-4 sample counts (64 coarse + 128 importance -> the fine pass evaluates 192 samples per
+  ray, 10 source views): 192 does not divide the 128-row attention tile, so the ray transformer runs in the
+  SIMT kernel on the bf16 tile images; compared with the fp32 staged path of the same library."""
+  cfg = dict(mono=False, H=36, W=64, V_dy=10, V_st=10, rays=48, N_samples=64, N_importance=128, num_vv=0,
+             inv_uniform=True, anti_alias_pooling=1, mask_rgb=0, seed=33, stress=False)
+  ref = _run_mode(cfg, "fp32")["outputs_fine_ref"]
+  got = _run_mode(cfg, "bf16")["outputs_fine_ref"]
+  assert got["weights"].shape[-1] == 192
+  assert_close_frac("rgb", got["rgb"], ref["rgb"], rtol=0, atol=2e-3, max_bad_frac=0.03)
+  assert_close_frac("weights", got["weights"], ref["weights"], rtol=0, atol=2e-3, max_bad_frac=0.03)
+
+
 def test_more_than_16_views_falls_back_to_staged_tensor_core_layers():
   cfg = dict(mono=False, H=36, W=64, V_dy=7, V_st=18, rays=64, N_samples=16, N_importance=16, num_vv=0,
              inv_uniform=True, anti_alias_pooling=1, mask_rgb=0, seed=32, stress=False)
