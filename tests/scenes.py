@@ -24,6 +24,12 @@ GOLDEN_CONFIGS = {
                        N_samples=32, N_importance=0, num_vv=2, inv_uniform=True,
                        anti_alias_pooling=1, mask_rgb=1, seed=14, stress=False,
                        anchor_offset=2, occ_weights_mode=0),
+    # same branch with the anchor one frame away: occ_weights_mode 0 then takes the "full" disocclusion
+    # score (render_ray.py:1233-1242), the other arm of the mode switch
+    "mono_train_near": dict(mono=True, H=36, W=64, V_dy=8, V_st=4, rays=16,
+                            N_samples=32, N_importance=0, num_vv=2, inv_uniform=True,
+                            anti_alias_pooling=1, mask_rgb=1, seed=15, stress=False,
+                            anchor_offset=-1, occ_weights_mode=0),
 }
 
 
