@@ -1,0 +1,39 @@
+"""The reference arm of bench.py (the oracle port timed on host cores) runs without a GPU and prints ONE JSON
+line with the keys the driver reads; the product arm refuses to run without CUDA (no CPU fallback)."""
+
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+  env = dict(os.environ, OMP_NUM_THREADS="4")
+  return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT, env=env,
+                        capture_output=True, text=True, timeout=600)
+
+
+def test_reference_arm_prints_the_contract_line():
+  p = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-rays", "8")
+  assert p.returncode == 0, p.stderr[-2000:]
+  lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["higher_is_better"] is True
+  assert d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["value"] > 0
+  assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+  assert d["cpu_baseline"]["value"] == d["value"]
+  assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+  assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_product_arm_fails_loudly_without_cuda():
+  if torch.cuda.is_available():
+    return  # on a GPU box the product arm is exercised by the driver itself
+  p = _run("--steps", "1", "--warmup", "1")
+  assert p.returncode != 0
+  assert "cuda" in (p.stderr + p.stdout).lower()
