@@ -52,6 +52,8 @@ def parse():
   ap.add_argument("--ref-rays", type=int, default=64, help="rays per step of the CPU reference arm")
   ap.add_argument("--cpu-rays", type=int, default=64, help="rays of the cpu_baseline sample")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--view-kernel", default="quad", choices=["quad", "twin"],
+                  help="per-view stage kernel: quad schedule (default) or the round-1 twin-warp kernel")
   return ap.parse_args()
 
 
@@ -185,6 +187,7 @@ def main():
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
   rr.set_precision(a.precision)
+  _lib.lib.dyn_debug_set_view_kernel(1 if a.view_kernel == "twin" else 0)
 
   # every rank renders its own bundle of rays of the same scene (ray shard = rank)
   # every rank renders `rays` rays of its own target view of the same scene

@@ -106,8 +106,8 @@ size_t dyn_net_param_count(int kind) {
 
 size_t dyn_net_packed_bytes(int kind) {
   switch (kind) {
-    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes + fused_view_bytes(kind) + view_twin_bytes(kind) + fused_chain_bytes(kind);
-    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes + fused_view_bytes(kind) + view_twin_bytes(kind) + fused_chain_bytes(kind);
+    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes + view_twin_bytes(kind) + view_quad_bytes(kind) + fused_chain_bytes(kind);
+    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes + view_twin_bytes(kind) + view_quad_bytes(kind) + fused_chain_bytes(kind);
     case DYN_NET_MOTION: return (size_t)motion_layout(8).all.packed_bytes + fused_chain_bytes(kind);
     default: return 0;
   }
@@ -171,10 +171,10 @@ int dyn_net_create(int kind, const float* params, size_t n_params, void* packed,
       int rc = e == cudaSuccess ? DYN_OK : fail(DYN_E_CUDA, "reading parameters back: %s", cudaGetErrorString(e));
       char* cur = reinterpret_cast<char*>(packed) + ll.packed_bytes;
       if (!rc && kind != DYN_NET_MOTION) {
-        rc = fused_view_build(n, hp, cur, fused_view_bytes(kind), (cudaStream_t)stream);
-        cur += fused_view_bytes(kind);
-        if (!rc) rc = view_twin_build(n, hp, cur, view_twin_bytes(kind), (cudaStream_t)stream);
+        rc = view_twin_build(n, hp, cur, view_twin_bytes(kind), (cudaStream_t)stream);
         cur += view_twin_bytes(kind);
+        if (!rc) rc = view_quad_build(n, hp, cur, view_quad_bytes(kind), (cudaStream_t)stream);
+        cur += view_quad_bytes(kind);
       }
       if (!rc) rc = fused_chain_build(n, hp, cur, fused_chain_bytes(kind), (cudaStream_t)stream);
       free(hp);
@@ -205,6 +205,8 @@ int dyn_featmaps_channels_last(const float* featmaps, float* out, int V, int C, 
   DYN_CHECK_ARG(featmaps && out && V >= 1 && C >= 1 && h >= 1 && w >= 1);
   return launch_to_channels_last(featmaps, out, V, C, h * w, (cudaStream_t)stream);
 }
+
+void dyn_debug_set_view_kernel(int twin) { set_view_kernel(twin); }
 
 static long long* g_view_dbg = nullptr;
 void dyn_debug_set_view_timestamps(long long* dev_buf) { g_view_dbg = dev_buf; }

@@ -119,15 +119,13 @@ struct dyn_net {
   dyn::DynamicLayout dl;
   dyn::StaticLayout sl;
   dyn::MotionLayout ml;
-  // fused per-view tensor-core stage (nets_fused.cu): weight images + chunk table
-  void* fused_img;
-  void* fused_tab;
-  int fused_nchunks;
   // row-local fused chains (chains_fused.cu): motion: [0]; aggregation nets:
   // [0] point stage 1, [1] point stage 2, [2] static blending head
   dyn::ChainImage chain[3];
   // twin-warp per-view stage (view_twin.cu): weight images in its column layout
   dyn::ChainImage twin;
+  // quad-schedule per-view stage (view_quad.cu)
+  dyn::ChainImage quad;
 };
 
 // ---- device helpers ---------------------------------------------------------

@@ -1,6 +1,6 @@
-// Host-side dispatch of the fused per-(point, view) stage of the two aggregation networks.
-// The kernel itself is the twin-warp one in view_twin.cu (the earlier one-thread-per-row
-// kernel was removed once the twin-warp version superseded it; see profiles/r01_kernels.md).
+// Host-side dispatch of the fused per-(point, view) stage of the two aggregation networks: argument
+// block + choice between the quad-schedule kernel (view_quad.cu, default) and the twin-warp kernel of
+// round 1 (view_twin.cu, kept for comparison and for the phase-timestamp profiling hook).
 //
 // Reference semantics: ibrnet/projection.py:103-176, ibrnet/mlp_network.py:236-284
 // (dynamic) and :423-497 (static).
@@ -12,13 +12,16 @@
 
 namespace dyn {
 
-// no separate image for the removed kernel (kept so dyn_net_packed_bytes' layout code is unchanged)
-size_t fused_view_bytes(int kind) { (void)kind; return 0; }
-int fused_view_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes,
-                     cudaStream_t st) {
-  (void)host_params; (void)dst_dev; (void)dst_bytes; (void)st;
-  n->fused_img = nullptr; n->fused_tab = nullptr; n->fused_nchunks = 0;
-  return DYN_OK;
+// DYN_VIEW_KERNEL=twin selects the two-CTAs-per-SM kernel of round 1 (view_twin.cu); the default is the
+// quad schedule (view_quad.cu).  Read once per process.
+static int g_view_kernel = -1;  // 0 quad, 1 twin
+void set_view_kernel(int twin) { g_view_kernel = twin ? 1 : 0; }
+static bool use_twin_kernel() {
+  if (g_view_kernel < 0) {
+    const char* e = getenv("DYN_VIEW_KERNEL");
+    g_view_kernel = (e != nullptr && e[0] == 't') ? 1 : 0;
+  }
+  return g_view_kernel == 1;
 }
 
 int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st) {
@@ -38,7 +41,8 @@ int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
     a.o_w8 = L.vis2_2.w; a.o_b8 = L.vis2_2.b; a.o_s = -1;
     a.anti_alias = 0; a.mask_rgb = 0;
   }
-  return launch_view_twin(n, a, V, st);
+  if (use_twin_kernel() || a.dbg != nullptr) return launch_view_twin(n, a, V, st);
+  return launch_view_quad(n, a, V, st);
 }
 
 }  // namespace dyn

@@ -251,6 +251,11 @@ int dyn_debug_pack_layer(const float* W, const float* bias, int N, int Kw, int N
  * 128-row tile: the layout activations use between the fused kernels. */
 size_t dyn_debug_tile_image_off(long long row, int kgroup, int kgroups);
 
+/* comparison hook: 0 (default) runs the fused per-view stage with the quad-schedule kernel
+ * (csrc/view_quad.cu), 1 with the twin-warp kernel of round 1 (csrc/view_twin.cu); the environment
+ * variable DYN_VIEW_KERNEL=twin sets the initial value. */
+void dyn_debug_set_view_kernel(int twin);
+
 /* profiling hook: when set, block 0 of the fused static per-view kernel writes clock64()
  * phase timestamps ([2 twins][64]) into dev_buf (profiles/scripts/prof_phases.py). */
 void dyn_debug_set_view_timestamps(long long* dev_buf);
