@@ -48,6 +48,7 @@ SIGNATURES = {
     "dyn_project_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i,
                                 _vp, _vp, _vp, _vp, _vp]),
     "dyn_compute_projections": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "dyn_compute_angle": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "dyn_plucker_ref": (_i, [_vp, _vp, _i, _vp, _vp]),
     "dyn_plucker_src": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "dyn_net_workspace_bytes": (_sz, [_i, _i, _i, _i]),

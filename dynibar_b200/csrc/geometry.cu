@@ -542,6 +542,14 @@ int dyn_points_from_depths(const float* ray_o, const float* ray_d, const float* 
   return DYN_OK;
 }
 
+// trajectory_basis[f] with Python indexing: the reference indexes the [T,nb] basis tensor with
+// ref_frame_idx + offset, and negative indices wrap (render_ray.py:479-497); only f < -T or f >= T fail
+static inline bool wrap_frame(int f, int T, int* out) {
+  if (f < -T || f >= T) return false;
+  *out = f < 0 ? f + T : f;
+  return true;
+}
+
 int dyn_traj_displace(const float* pts, const float* coeff, const float* basis, int T, int nb,
                       int frame_idx, const int* offsets_host, int n_off, int num_vv, int R, int S,
                       float* pts_seq, void* stream) {
@@ -554,15 +562,16 @@ int dyn_traj_displace(const float* pts, const float* coeff, const float* basis, 
   TrajArgs a;
   memset(&a, 0, sizeof(a));
   a.n_off = n_off; a.num_vv = num_vv; a.nb = nb;
-  DYN_CHECK_ARG(frame_idx >= 0 && frame_idx < T);
+  int f0 = 0;
+  DYN_CHECK_ARG(wrap_frame(frame_idx, T, &f0));
   for (int v = 0; v < n_off; ++v) {
-    int f = frame_idx + offsets_host[v];
-    DYN_CHECK_ARG(f >= 0 && f < T);
+    int f = 0;
+    DYN_CHECK_ARG(wrap_frame(frame_idx + offsets_host[v], T, &f));
     int rc = fetch_small(basis + (size_t)f * nb, nb, hb + 8 * v, st);
     if (rc) return rc;
   }
   {
-    int rc = fetch_small(basis + (size_t)frame_idx * nb, nb, hb + 8 * n_off, st);
+    int rc = fetch_small(basis + (size_t)f0 * nb, nb, hb + 8 * n_off, st);
     if (rc) return rc;
   }
   for (int v = 0; v < n_off; ++v)
@@ -583,9 +592,10 @@ int dyn_traj_delta(const float* coeff, const float* basis, int T, int nb, const 
   static thread_local DeltaArgs a;
   a.n = n; a.nb = nb;
   for (int v = 0; v < n; ++v) {
-    DYN_CHECK_ARG(frames_a_host[v] >= 0 && frames_a_host[v] < T && frames_b_host[v] >= 0 && frames_b_host[v] < T);
-    int rc = fetch_small(basis + (size_t)frames_a_host[v] * nb, nb, a.ba[v], st);
-    if (!rc) rc = fetch_small(basis + (size_t)frames_b_host[v] * nb, nb, a.bb[v], st);
+    int fa = 0, fb = 0;
+    DYN_CHECK_ARG(wrap_frame(frames_a_host[v], T, &fa) && wrap_frame(frames_b_host[v], T, &fb));
+    int rc = fetch_small(basis + (size_t)fa * nb, nb, a.ba[v], st);
+    if (!rc) rc = fetch_small(basis + (size_t)fb * nb, nb, a.bb[v], st);
     if (rc) return rc;
   }
   long long N = (long long)R * S;
@@ -642,6 +652,41 @@ int dyn_compute_projections(const float* xyz, const float* src_cams, int V, int 
   return DYN_OK;
 }
 
+// compute_angle (projection.py:61-101): a = normalize(cam_tgt - x_st), b = normalize(cam_src_v - x_v),
+// out = [normalize(a - b), a . b]; xyz_st is [N,3] (st_views == 1, broadcast over the views) or [V,N,3]
+__global__ void compute_angle_kernel(const float* __restrict__ xyz_st, int st_views,
+                                     const float* __restrict__ xyz, const __grid_constant__ ViewCams cams,
+                                     int V, long long N, float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * V) return;
+  const int v = (int)(idx / N);
+  const long long pt = idx - (long long)v * N;
+  const float* s = xyz_st + ((st_views > 1 ? (long long)v * N : 0) + pt) * 3;
+  const float* q = xyz + idx * 3;
+  float a0 = cams.tgt[0] - s[0], a1 = cams.tgt[1] - s[1], a2 = cams.tgt[2] - s[2];
+  normalize3(a0, a1, a2);
+  float b0 = cams.center[v][0] - q[0], b1 = cams.center[v][1] - q[1], b2 = cams.center[v][2] - q[2];
+  normalize3(b0, b1, b2);
+  float d0 = a0 - b0, d1 = a1 - b1, d2 = a2 - b2;
+  const float dot = a0 * b0 + a1 * b1 + a2 * b2;
+  normalize3(d0, d1, d2);
+  reinterpret_cast<float4*>(out)[idx] = make_float4(d0, d1, d2, dot);
+}
+
+int dyn_compute_angle(const float* xyz_st, int st_views, const float* xyz, const float* query_cam,
+                      const float* src_cams, int V, int N, float* ray_diff, void* stream) {
+  DYN_CHECK_ARG(N >= 0 && V >= 1 && (st_views == 1 || st_views == V));
+  if (N == 0) return DYN_OK;
+  DYN_CHECK_ARG(xyz_st && xyz && query_cam && src_cams && ray_diff);
+  cudaStream_t st = (cudaStream_t)stream;
+  ViewCams vc;
+  int rc = build_view_cams(src_cams, V, query_cam, st, &vc);
+  if (rc) return rc;
+  compute_angle_kernel<<<cdiv((long long)N * V, 256), 256, 0, st>>>(xyz_st, st_views, xyz, vc, V, N, ray_diff);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
 int dyn_plucker_ref(const float* ray_o, const float* ray_d, int R, float* out6, void* stream) {
   if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
   DYN_CHECK_ARG(ray_o && ray_d && out6 && R >= 0);
@@ -683,11 +728,13 @@ int dyn_flow_sceneflow(const float* weights, const float* pts_seq, const float* 
     if (rc) return rc;
   }
   if (exp_sf != nullptr) {
-    DYN_CHECK_ARG(coeff && basis && frame_idx - sf_k >= 0 && frame_idx + sf_k < T);
+    int fp = 0, fm = 0, f0 = 0;
+    DYN_CHECK_ARG(coeff && basis && wrap_frame(frame_idx + sf_k, T, &fp) && wrap_frame(frame_idx - sf_k, T, &fm) &&
+                  wrap_frame(frame_idx, T, &f0));
     float hb[24];
-    int rc = fetch_small(basis + (size_t)(frame_idx + sf_k) * nb, nb, hb, st);
-    if (!rc) rc = fetch_small(basis + (size_t)(frame_idx - sf_k) * nb, nb, hb + 8, st);
-    if (!rc) rc = fetch_small(basis + (size_t)frame_idx * nb, nb, hb + 16, st);
+    int rc = fetch_small(basis + (size_t)fp * nb, nb, hb, st);
+    if (!rc) rc = fetch_small(basis + (size_t)fm * nb, nb, hb + 8, st);
+    if (!rc) rc = fetch_small(basis + (size_t)f0 * nb, nb, hb + 16, st);
     if (rc) return rc;
     for (int k = 0; k < nb; ++k) { fc.b_p[k] = hb[k]; fc.b_m[k] = hb[8 + k]; fc.b_0[k] = hb[16 + k]; }
   }

@@ -41,7 +41,7 @@ int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
     a.o_w8 = L.vis2_2.w; a.o_b8 = L.vis2_2.b; a.o_s = -1;
     a.anti_alias = 0; a.mask_rgb = 0;
   }
-  if (use_twin_kernel() || a.dbg != nullptr) return launch_view_twin(n, a, V, st);
+  if (use_twin_kernel()) return launch_view_twin(n, a, V, st);
   return launch_view_quad(n, a, V, st);
 }
 

@@ -511,7 +511,7 @@ struct QuadOps {
 };
 
 template <int VP, bool ST>
-__global__ void __maxnreg__(112) view_quad_kernel(const __grid_constant__ ViewFusedArgs a) {
+__global__ void __launch_bounds__(576, 1) view_quad_kernel(const __grid_constant__ ViewFusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem + 2 * kQATile;
   float* cst = reinterpret_cast<float*>(ring + kQRing * kQStage);
@@ -553,7 +553,8 @@ __global__ void __maxnreg__(112) view_quad_kernel(const __grid_constant__ ViewFu
   if (warp == W_PROD) {
     if ((tid & 31) == 0) producer_loop<true, kQRing, kQStage>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
   } else if (warp == W_ISSUE) {
-    issuer_loop<true, 2, kQRing, kQStage>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kQATile, nullptr);
+    issuer_loop<true, 2, kQRing, kQStage>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kQATile,
+                                          a.dbg ? a.dbg + 256 : nullptr);
   } else {
     QuadOps<VP, ST> ops{a, cst, warp >> 2, warp & 3, (warp & 3) * 32 + (tid & 31), 0, 0, a.w_img, a.h_img, false};
     ops.v = ops.r % VP;
@@ -568,37 +569,64 @@ __global__ void __maxnreg__(112) view_quad_kernel(const __grid_constant__ ViewFu
     c1.b_ready = bar_aready(bar0, 1, kQRing); c1.b_acc = bar_acc(bar0, 1, kQRing);
     c0.acc_cnt = 0; c1.acc_cnt = 0;
 
+    // profiling hook (dyn_debug_set_view_timestamps): clock64() of block 0, row 0 of every quad
+    int dbg_n = 0;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && ops.r == 0;
+#define TS()                                                              \
+  do {                                                                    \
+    if (dbg_on && dbg_n < 64) a.dbg[ops.q * 64 + dbg_n++] = clock64();    \
+  } while (0)
     for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
+      TS();  // 0
       if (ST) {
         ops.geometry(c0, it, 0);
         ops.gather_issue(c0);
+        TS();  // 1
         ops.geometry(c1, it, 1);     // tile 0: taps in flight, ray_dir_fc.0 on the tensor cores
+        TS();  // 2
         ops.gather_consume(c0);
         ops.gather_issue(c1);
+        TS();  // 3
         ops.f1_epilogue(c0);         // tile 1: taps in flight
+        TS();  // 4
         ops.gather_consume(c1);
         ops.f1_epilogue(c1);
+        TS();  // 5
       } else {
         ops.geometry(c0, it, 0);
         ops.gather_issue(c0);
         ops.geometry(c1, it, 1);
         ops.gather_consume(c0);
         ops.gather_issue(c1);
+        TS();  // 1
       }
       ops.pool1(c0);
+      TS();  // 6 (dynamic: 2)
       if (!ST) ops.gather_consume(c1);
       ops.pool1(c1);
+      TS();  // 7
       ops.f3_epilogue(c0);
+      TS();  // 8
       ops.f3_epilogue(c1);
+      TS();  // 9
       ops.f4_epilogue(c0);
+      TS();  // 10
       ops.f4_epilogue(c1);
+      TS();  // 11
       ops.f5_epilogue(c0, 0);
+      TS();  // 12
       ops.f5_epilogue(c1, 1);
+      TS();  // 13
       ops.f6_epilogue(c0, it, 0);
+      TS();  // 14
       ops.f6_epilogue(c1, it, 1);
+      TS();  // 15
       ops.f7_pool2(c0, 0);
+      TS();  // 16
       ops.f7_pool2(c1, 1);
+      TS();  // 17
     }
+#undef TS
   }
   __syncthreads();
   if (warp == W_ISSUE) {
@@ -711,7 +739,6 @@ int launch_view_quad(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st)
   a.chunks = n->quad.tab;
   a.nchunks = n->quad.nchunks;
   a.ablate = 0;
-  a.dbg = nullptr;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;

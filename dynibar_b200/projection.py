@@ -39,9 +39,23 @@ class Projector(object):
     return pix.reshape(shape + (2,)), front.bool().reshape(shape)
 
   def compute_angle(self, xyz_st, xyz, query_camera, train_cameras):
-    """Not exposed separately by the library: ray_diff is produced by the fused
-    gather kernel.  Provided through compute_with_motions."""
-    raise NotImplementedError("use compute_with_motions (ray_diff is fused into the gather kernel)")
+    """projection.py:61-101.  xyz_st [V or 1, ..., 3] (the reference passes the static point
+    expanded over the views), xyz [V,...,3], query_camera [34], train_cameras [V,34]
+    -> ray_diff [V,...,4] = [normalize(a - b), a . b]."""
+    shape = xyz.shape[:-1]
+    V = shape[0]
+    x = f32c(xyz).reshape(V, -1, 3)
+    N = x.shape[1]
+    st_views = xyz_st.shape[0]
+    assert st_views in (1, V), "xyz_st must have 1 or n_views leading entries"
+    xs = f32c(xyz_st).reshape(st_views, -1, 3)
+    assert xs.shape[1] == N
+    out = torch.empty(V, N, 4, device=x.device)
+    A = Args()
+    with torch.cuda.device(x.device):
+      check(lib.dyn_compute_angle(ptr(xs), st_views, ptr(x), A.host(query_camera.reshape(-1)),
+                                  A.host(train_cameras), V, N, ptr(out), stream()))
+    return out.reshape(shape + (4,))
 
   def compute_with_motions(self, xyz_st, xyz, query_camera, train_imgs, train_cameras, featmaps):
     """projection.py:103-176.

@@ -40,6 +40,21 @@ def _no_grad_only(*tensors):
         "call under torch.no_grad() with detached inputs")
 
 
+def _refuse_training(model, *featmaps):
+  """The orchestrators run under no_grad (forward-only kernels): a training loop that swapped the
+  import would get detached outputs and fail late (or silently).  Fail loudly instead."""
+  if not torch.is_grad_enabled():
+    return
+  mods = [m for m in vars(model).values() if isinstance(m, torch.nn.Module)]
+  live = any(p.requires_grad for m in mods for p in m.parameters())
+  live = live or any(torch.is_tensor(f) and f.requires_grad for fm in featmaps if fm is not None
+                     for f in fm if f is not None)
+  if live:
+    raise NotImplementedError(
+        "dynibar_b200 kernels are forward-only (training backward = SURVEY 8(f) f2): parameters or "
+        "feature maps require grad; call under torch.no_grad() or freeze them")
+
+
 def _scalar(x):
   return float(x.reshape(-1)[0]) if torch.is_tensor(x) else float(x)
 
@@ -126,6 +141,9 @@ def motion_coefficients(module, pts, t):
   with torch.cuda.device(dev):
     check(lib.dyn_motion_coeffs(net.handle, A(pts), float(t), R, S, ptr(out),
                                 ws.data_ptr(), nbytes, PRECISION, stream()))
+  div = float(getattr(_weights.de_parallel(module), "sf_mag_div", 1.0))
+  if div != 1.0:  # MotionMLP.forward divides its output (mlp_network.py:617)
+    out = out / div
   return out
 
 
@@ -462,6 +480,7 @@ def render_rays_mv(frame_idx, time_embedding, time_offset, ray_batch, model, pro
   Returns the reference's dict: outputs_coarse_ref, outputs_fine_ref,
   outputs_fine_ref_dy, outputs_fine_anchor(None), outputs_fine_anchor_dy(None)."""
   assert N_importance > 0  # render_ray.py:787
+  _refuse_training(model, coarse_featmaps, fine_featmaps)
   with torch.no_grad():
     t = _scalar(time_embedding[0].float())
     offs = [int(o) for o in time_offset[0]]
@@ -493,6 +512,7 @@ def render_rays_mono(frame_idx, time_embedding, time_offset, ray_batch, model, f
   """Coarse-only rendering for monocular video (render_ray.py:870-1277), including the
   cross-time branch (:1099-1270) when is_train=True.  Forward only: the kernels have no
   backward yet, so everything runs under no_grad (training needs SURVEY 8(f) f2)."""
+  _refuse_training(model, featmaps)
   with torch.no_grad():
     t = _scalar(time_embedding[0].float())
     ray_batch, hb = _with_host_copies(ray_batch, model, ("trajectory_basis",))

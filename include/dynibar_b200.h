@@ -139,6 +139,13 @@ int dyn_project_gather(const float* xyz_st, const float* xyz,
 int dyn_compute_projections(const float* xyz, const float* src_cams, int V,
                             int N, float* pix, uint8_t* front, void* stream);
 
+/* compute_angle only (projection.py:61-101): xyz_st [st_views,N,3] with st_views 1 (same reference
+ * point for every view) or V; xyz [V,N,3]; ray_diff [V,N,4] = [normalize(a - b), a . b] with
+ * a = normalize(c_tgt - xyz_st), b = normalize(c_src_v - xyz_v). */
+int dyn_compute_angle(const float* xyz_st, int st_views, const float* xyz,
+                      const float* query_cam, const float* src_cams, int V, int N,
+                      float* ray_diff, void* stream);
+
 /* ---- a7: Plucker coordinates, render_ray.py:372-396 ---------------------- */
 int dyn_plucker_ref(const float* ray_o, const float* ray_d, int R, float* out6,
                     void* stream);

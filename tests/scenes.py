@@ -44,3 +44,36 @@ def build(cfg, sigma_bias=-4.0):
                                      args=args, seed=cfg["seed"],
                                      mono=cfg["mono"], sigma_bias=sigma_bias)
   return batch, feat_c, feat_f, frame, t, offs, model, args
+
+
+# ---- frame-level fixtures (tests/golden/make_golden_frame.py) ----------------------------------
+FRAME_CONFIGS = {
+    # render_single_image_nvi (render_image.py:9-217): a whole 12x16 frame in chunks of 50 rays
+    "frame_nvi": dict(GOLDEN_CONFIGS["mv_small"], H=12, W=16, rays=None, chunk=50),
+    # render_single_image_mono (render_image.py:220-439), is_train=True (cross-time branch included)
+    "frame_mono": dict(GOLDEN_CONFIGS["mono_train"], H=12, W=16, rays=None, chunk=70),
+}
+# occlusion-weight modes 1 and 2 of the cross-time branch (render_ray.py:1243-1252)
+OCC_MODE_CONFIGS = {
+    "occ_mode1": dict(GOLDEN_CONFIGS["mono_train"], rays=12, occ_weights_mode=1),
+    "occ_mode2": dict(GOLDEN_CONFIGS["mono_train"], rays=12, occ_weights_mode=2),
+}
+
+
+def sampler_data(batch, H, W, seed, n_flow=6):
+  """The per-frame `data` dict a dataset hands to RaySamplerSingleImage (sample_ray.py:50-141):
+  cameras and source views from the scene + seeded per-pixel supervision."""
+  g = torch.Generator().manual_seed(seed + 500)
+  data = {k: batch[k] for k in ("camera", "depth_range", "src_rgbs", "src_cameras", "static_src_rgbs",
+                                "static_src_cameras")}
+  for k in ("anchor_camera", "anchor_src_rgbs", "anchor_src_cameras"):
+    if k in batch:
+      data[k] = batch[k]
+  data["rgb_path"] = "synthetic"
+  data["rgb"] = torch.rand(1, H, W, 3, generator=g)
+  data["disp"] = torch.rand(1, H, W, generator=g)
+  data["motion_mask"] = (torch.rand(1, H, W, generator=g) > 0.5).float()
+  data["static_mask"] = 1.0 - data["motion_mask"]
+  data["flows"] = torch.randn(1, n_flow, H, W, 2, generator=g)
+  data["masks"] = (torch.rand(1, n_flow, H, W, generator=g) > 0.3).float()
+  return data

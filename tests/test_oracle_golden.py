@@ -79,6 +79,21 @@ def test_oracle_matches_golden(name, golden):
     _cmp("raw_" + br, aux["raw_" + br][valid], st["raw_" + br][valid])
 
 
+@pytest.mark.parametrize("name", list(scenes.OCC_MODE_CONFIGS))
+def test_oracle_occlusion_weight_modes_match_golden(name, golden):
+  """occ_weights_mode 1 / 2 of the cross-time branch (render_ray.py:1243-1252)."""
+  fx = golden("occ_modes")[name]
+  cfg = fx["cfg"]
+  batch, feat_c, feat_f, frame, t, offs, model, args = scenes.build(cfg)
+  assert abs(_checksum(batch, [feat_c, feat_f]) - fx["checksum"]) < 1e-6 * fx["checksum"]
+  with torch.no_grad():
+    ret = orc.render_rays_mono(frame, t, offs, batch, model, feat_c, None, cfg["N_samples"], args,
+                               inv_uniform=cfg["inv_uniform"], det=True, is_train=True, num_vv=cfg["num_vv"])
+  for k in ("outputs_coarse_anchor", "outputs_coarse_anchor_dy"):
+    for kk, want in fx[k].items():
+      _cmp("%s/%s" % (k, kk), ret[k][kk], want)
+
+
 def test_oracle_random_sampling_matches_golden(golden):
   """det=False: the oracle takes the reference's random draws as inputs."""
   fx = golden("mv_small")

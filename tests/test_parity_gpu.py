@@ -74,6 +74,13 @@ def test_stages_against_golden(rr, golden, name):
   assert_close_frac("mask_dy", mk, st["mask_dy"], max_bad_frac=1e-3)
   assert_close_frac("rgb_feat_dy", f, st["rgb_feat_dy"], rtol=1e-4, atol=2e-5, max_bad_frac=1e-3)
   _cmp_ray_diff("ray_diff_dy", rd, st["ray_diff_dy"])
+  # the public compute_angle (projection.py:61-101), called the way compute_with_motions calls it
+  # (static point expanded over the views) and with the un-expanded point
+  seq_d = _dev(st["seq"])
+  for xyz_st in (pts[None].expand(seq_d.shape[0], -1, -1, -1), pts[None]):
+    ang = P.compute_angle(xyz_st, seq_d, b["camera"][0], b["src_cameras"][0])
+    assert ang.shape == seq_d.shape[:-1] + (4,)
+    _cmp_ray_diff("compute_angle", ang.permute(1, 2, 0, 3), st["ray_diff_dy"])
   V_st = b["static_src_rgbs"].shape[1]
   f, rd, mk = P.compute_with_motions(pts, pts[None].repeat(V_st, 1, 1, 1), b["camera"],
                                      b["static_src_rgbs"], b["static_src_cameras"], fc[2])
