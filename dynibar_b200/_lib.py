@@ -56,6 +56,7 @@ SIGNATURES = {
     "dyn_net_static": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "dyn_net_fused_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "dyn_featmaps_channels_last": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "dyn_rgbs_rgba": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dyn_net_static_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i,
                                   _i, _vp, _vp, _vp, _sz, _vp]),
     "dyn_net_dynamic_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i,

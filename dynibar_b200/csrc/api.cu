@@ -200,13 +200,18 @@ size_t dyn_net_fused_workspace_bytes(int kind, int R, int S, int V) {
   return net_fused_workspace(kind, R, S, V);
 }
 
-int dyn_featmaps_channels_last(const float* featmaps, float* out, int V, int C, int h, int w,
+int dyn_featmaps_channels_last(const float* featmaps, void* out_bf16, int V, int C, int h, int w,
                                void* stream) {
-  DYN_CHECK_ARG(featmaps && out && V >= 1 && C >= 1 && h >= 1 && w >= 1);
-  return launch_to_channels_last(featmaps, out, V, C, h * w, (cudaStream_t)stream);
+  DYN_CHECK_ARG(featmaps && out_bf16 && V >= 1 && C >= 1 && h >= 1 && w >= 1);
+  return launch_to_channels_last_bf16(featmaps, out_bf16, V, C, h * w, (cudaStream_t)stream);
 }
 
-void dyn_debug_set_view_kernel(int twin) { set_view_kernel(twin); }
+int dyn_rgbs_rgba(const float* src_rgbs, float* out_rgba, int V, int H, int W, void* stream) {
+  DYN_CHECK_ARG(src_rgbs && out_rgba && V >= 1 && H >= 1 && W >= 1);
+  return launch_rgb_to_rgba(src_rgbs, out_rgba, (long long)V * H * W, (cudaStream_t)stream);
+}
+
+void dyn_debug_set_view_kernel(int quad) { set_view_kernel(quad); }
 
 static long long* g_view_dbg = nullptr;
 void dyn_debug_set_view_timestamps(long long* dev_buf) { g_view_dbg = dev_buf; }
@@ -214,7 +219,7 @@ long long* view_dbg_ptr() { return g_view_dbg; }
 
 int dyn_net_static_fused(dyn_net_t net, const float* pts, const float* ray_o, const float* ray_d,
                          const float* query_cam, const float* src_rgbs, const float* src_cams,
-                         const float* feat_cl, int R, int S, int V, int H, int W, int C, int h, int w,
+                         const void* feat_cl, int R, int S, int V, int H, int W, int C, int h, int w,
                          float* raw, float* mask_out, void* workspace, size_t workspace_bytes,
                          void* stream) {
   if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)
@@ -228,7 +233,7 @@ int dyn_net_static_fused(dyn_net_t net, const float* pts, const float* ray_o, co
 
 int dyn_net_dynamic_fused(dyn_net_t net, const float* pts, const float* pts_seq, const float* ray_dir,
                           const float* query_cam, const float* src_rgbs, const float* src_cams,
-                          const float* feat_cl, float time, int R, int S, int V, int H, int W, int C,
+                          const void* feat_cl, float time, int R, int S, int V, int H, int W, int C,
                           int h, int w, float* raw, float* mask_out, void* workspace,
                           size_t workspace_bytes, void* stream) {
   if (R == 0) return DYN_OK;  // empty batch: nothing to do (pointers may be null)

@@ -2,6 +2,8 @@
 // projection + bilinear gather + view-angle difference (a4-a6), Plucker
 // coordinates (a7), optical flow / expected scene flow (a14).
 // All fp32.  Reference file:line citations are relative to /root/reference.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "geometry.cuh"
 
@@ -162,6 +164,34 @@ __global__ void to_channels_last_kernel(const float* __restrict__ in, float* __r
     int p = p0 + j, c = c0 + threadIdx.x;
     if (c < C && p < hw) dst[(long long)p * C + c] = tile[threadIdx.x][j];
   }
+}
+
+// The fused per-view kernels read the source views in two packed per-frame layouts:
+//   feature maps [V,C,h,w] fp32 -> channels-last bf16 [V,h,w,C]: one bilinear tap of all 32 channels
+//     = 64 contiguous bytes (the operands of the per-view layers are bf16 anyway);
+//   source images [V,H,W,3] fp32 -> [V,H,W,4] fp32 (alpha = 0): one tap = ONE aligned 16-byte load
+//     instead of three 4-byte loads (colours stay fp32: the blending head outputs them directly).
+__global__ void to_channels_last_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                             int C, int hw) {
+  __shared__ float tile[32][33];
+  int v = blockIdx.z;
+  int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = in + (long long)v * C * hw;
+  __nv_bfloat16* dst = out + (long long)v * C * hw;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, p = p0 + threadIdx.x;
+    if (c < C && p < hw) tile[j][threadIdx.x] = src[(long long)c * hw + p];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int p = p0 + j, c = c0 + threadIdx.x;
+    if (c < C && p < hw) dst[(long long)p * C + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+
+__global__ void rgb_to_rgba_kernel(const float* __restrict__ in, float4* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4(in[3 * i], in[3 * i + 1], in[3 * i + 2], 0.f);
 }
 
 // Stand-alone projection + gather (Projector.compute_with_motions).
@@ -484,6 +514,19 @@ int build_view_cams(const float* src_cams, int V, const float* query_cam, cudaSt
 int launch_to_channels_last(const float* featmaps, float* out, int V, int C, int hw, cudaStream_t st) {
   dim3 tb(32, 8), tg(cdiv(hw, 32), cdiv(C, 32), V);
   to_channels_last_kernel<<<tg, tb, 0, st>>>(featmaps, out, C, hw);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
+int launch_to_channels_last_bf16(const float* featmaps, void* out, int V, int C, int hw, cudaStream_t st) {
+  dim3 tb(32, 8), tg(cdiv(hw, 32), cdiv(C, 32), V);
+  to_channels_last_bf16_kernel<<<tg, tb, 0, st>>>(featmaps, reinterpret_cast<__nv_bfloat16*>(out), C, hw);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
+int launch_rgb_to_rgba(const float* rgbs, float* out, long long npix, cudaStream_t st) {
+  rgb_to_rgba_kernel<<<cdiv(npix, 256), 256, 0, st>>>(rgbs, reinterpret_cast<float4*>(out), npix);
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }

@@ -27,5 +27,7 @@ __device__ __forceinline__ void project_point(const float* P, float x, float y, 
 int build_view_cams(const float* src_cams, int V, const float* query_cam, cudaStream_t st,
                     ViewCams* vc);
 int launch_to_channels_last(const float* featmaps, float* out, int V, int C, int hw, cudaStream_t st);
+int launch_to_channels_last_bf16(const float* featmaps, void* out, int V, int C, int hw, cudaStream_t st);
+int launch_rgb_to_rgba(const float* rgbs, float* out, long long npix, cudaStream_t st);
 
 }  // namespace dyn

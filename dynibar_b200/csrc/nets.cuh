@@ -24,11 +24,11 @@ int motion_f32(const dyn_net* n, const float* x, int ldx, bool time_is_column, f
 size_t net_fused_workspace(int kind, int R, int S, int V);
 int net_static_fused(const dyn_net* n, const float* pts, const float* ray_o, const float* ray_d,
                      const float* query_cam, const float* src_rgbs, const float* src_cams,
-                     const float* feat_cl, int R, int S, int V, int H, int W, int h, int w, float* raw,
+                     const void* feat_cl, int R, int S, int V, int H, int W, int h, int w, float* raw,
                      float* mask_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int net_dynamic_fused(const dyn_net* n, const float* pts, const float* pts_seq, const float* ray_dir,
                       const float* query_cam, const float* src_rgbs, const float* src_cams,
-                      const float* feat_cl, float time, int R, int S, int V, int H, int W, int h, int w,
+                      const void* feat_cl, float time, int R, int S, int V, int H, int W, int h, int w,
                       float* raw, float* mask_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int debug_point_chain(const dyn_net* n, const float* G, const float* nvalid, const float* pts,
                       const float* ray_dir, int R, int S, float* g2, float* Q, float* K, float* V,

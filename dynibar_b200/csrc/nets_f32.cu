@@ -990,19 +990,19 @@ int debug_point_chain(const dyn_net* n, const float* G, const float* nvalid, con
 }
 
 static int fill_view_args(ViewFusedArgs* a, const float* query_cam, const float* src_rgbs,
-                          const float* src_cams, const float* feat_cl, int V, int S, int H, int W,
+                          const float* src_cams, const void* feat_cl, int V, int S, int H, int W,
                           int h, int w, cudaStream_t st) {
   memset(a, 0, sizeof(*a));
   RUN(build_view_cams(src_cams, V, query_cam, st, &a->cams));
   a->h_img = a->cams.h_img; a->w_img = a->cams.w_img;
-  a->rgbs = src_rgbs; a->feat_cl = feat_cl;
+  a->rgba = src_rgbs; a->feat_bf = reinterpret_cast<const uint16_t*>(feat_cl);
   a->H = H; a->W = W; a->h = h; a->w = w; a->V = V; a->S = S;
   return DYN_OK;
 }
 
 int net_static_fused(const dyn_net* n, const float* pts, const float* ray_o, const float* ray_d,
                      const float* query_cam, const float* src_rgbs, const float* src_cams,
-                     const float* feat_cl, int R_all, int S, int V, int H, int W, int h, int w,
+                     const void* feat_cl, int R_all, int S, int V, int H, int W, int h, int w,
                      float* raw, float* mask_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const StaticLayout& L = n->sl;
   const int prec = DYN_PREC_BF16;
@@ -1045,7 +1045,7 @@ int net_static_fused(const dyn_net* n, const float* pts, const float* ray_o, con
 
 int net_dynamic_fused(const dyn_net* n, const float* pts, const float* pts_seq, const float* ray_dir,
                       const float* query_cam, const float* src_rgbs, const float* src_cams,
-                      const float* feat_cl, float time, int R_all, int S, int V, int H, int W, int h,
+                      const void* feat_cl, float time, int R_all, int S, int V, int H, int W, int h,
                       int w, float* raw, float* mask_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const DynamicLayout& L = n->dl;
   const int prec = DYN_PREC_BF16;

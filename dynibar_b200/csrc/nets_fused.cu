@@ -1,6 +1,6 @@
 // Host-side dispatch of the fused per-(point, view) stage of the two aggregation networks: argument
-// block + choice between the quad-schedule kernel (view_quad.cu, default) and the twin-warp kernel of
-// round 1 (view_twin.cu, kept for comparison and for the phase-timestamp profiling hook).
+// block + choice between the twin-warp kernel (view_twin.cu, default) and the quad-schedule kernel
+// (view_quad.cu, kept for comparison).
 //
 // Reference semantics: ibrnet/projection.py:103-176, ibrnet/mlp_network.py:236-284
 // (dynamic) and :423-497 (static).
@@ -12,16 +12,17 @@
 
 namespace dyn {
 
-// DYN_VIEW_KERNEL=twin selects the two-CTAs-per-SM kernel of round 1 (view_twin.cu); the default is the
-// quad schedule (view_quad.cu).  Read once per process.
-static int g_view_kernel = -1;  // 0 quad, 1 twin
-void set_view_kernel(int twin) { g_view_kernel = twin ? 1 : 0; }
+// Two schedules of the same per-tile work: the twin-warp kernel (view_twin.cu: two independent CTAs per SM,
+// default -- it is the faster one, profiles/r02_view_kernels.md) and the quad kernel (view_quad.cu: one CTA
+// per SM alternating between two tiles; DYN_VIEW_KERNEL=quad or dyn_debug_set_view_kernel(1)).
+static int g_view_kernel = -1;  // 0 twin, 1 quad
+void set_view_kernel(int quad) { g_view_kernel = quad ? 1 : 0; }
 static bool use_twin_kernel() {
   if (g_view_kernel < 0) {
     const char* e = getenv("DYN_VIEW_KERNEL");
-    g_view_kernel = (e != nullptr && e[0] == 't') ? 1 : 0;
+    g_view_kernel = (e != nullptr && e[0] == 'q') ? 1 : 0;
   }
-  return g_view_kernel == 1;
+  return g_view_kernel == 0;
 }
 
 int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st) {

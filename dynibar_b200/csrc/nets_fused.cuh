@@ -24,8 +24,8 @@ struct ViewFusedArgs {
   const float* pts;       // [P,3] reference-time sample points
   const float* pts_seq;   // motion-displaced points, view v at pts_seq + v*seq_stride*3 (dynamic) or null
   long long seq_stride;
-  const float* rgbs;      // [V,H,W,3]
-  const float* feat_cl;   // [V,h,w,32] channels-last feature maps
+  const float* rgba;      // [V,H,W,4] fp32 source images, alpha = 0 (dyn_rgbs_rgba)
+  const uint16_t* feat_bf;  // [V,h,w,32] channels-last bf16 feature maps (dyn_featmaps_channels_last)
   const float* ref_feat;  // [R,35] static: ref_feature_fc(PE(ref plucker)) per ray
   const float* dfeat;     // [35] dynamic: time feature
   const float* params;    // fp32 parameter blob (biases, small heads)
@@ -135,7 +135,7 @@ size_t view_quad_bytes(int kind);
 int view_quad_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes, cudaStream_t st);
 int launch_view_quad(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st);
 
-void set_view_kernel(int twin);
+void set_view_kernel(int quad);
 int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st);
 
 }  // namespace dyn

@@ -87,9 +87,9 @@ struct QCtx {
   float pu, pv, mask_proj, mask, w1, vis1, rd[4];
   float ch[24];   // pooled channels of this quad (slot layout in view_quad_build)
   // bilinear taps in flight
-  float4 tf[8];   // 4 taps x 2 float4 (8 feature channels)
+  uint4 tf[4];    // 4 taps x 16 B (8 bf16 feature channels)
   float tw[4];    // tap weights (feature map)
-  float tr[12];   // 4 taps x rgb
+  float4 tr[4];   // 4 taps x RGBA
   float twr[4];   // tap weights (image)
 };
 
@@ -182,34 +182,27 @@ struct QuadOps {
     }
   }
 
-  // ---- issue the bilinear taps of this quad's 8 feature channels (+ rgb) ----
+  // ---- issue the bilinear taps of this quad's 8 feature channels (+ rgb): packed per-frame layouts
+  //      (bf16 channels-last features: one 16 B load per tap; RGBA fp32 images: one 16 B load per tap) ----
   __device__ __forceinline__ void gather_issue(QCtx& c) const {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) c.tf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 12; ++i) c.tr[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { c.tw[i] = 0.f; c.twr[i] = 0.f; }
-    if (!c.valid) return;
+    const int vc = c.valid ? v : 0;
     const float gx = 2.f * c.pu / (wh - 1.f) - 1.f, gy = 2.f * c.pv / (hh - 1.f) - 1.f;
     {
       const float fx = (gx + 1.f) * 0.5f * (float)(a.w - 1), fy = (gy + 1.f) * 0.5f * (float)(a.h - 1);
       const float x0f = floorf(fx), y0f = floorf(fy);
       const int x0 = (int)x0f, y0 = (int)y0f;
       const float ax = fx - x0f, ay = fy - y0f, bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
-      const float* base = a.feat_cl + (long long)v * a.h * a.w * kC + 8 * q;
+      const uint16_t* base = a.feat_bf + (long long)vc * a.h * a.w * kC + 8 * q;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-          // out-of-range taps load a clamped texel with weight 0 (no branch: all loads in flight together)
+          // out-of-range taps (and padding rows) load a clamped texel with weight 0 (no branch)
           const int xi = x0 + dx, yi = y0 + dy;
-          const bool in = xi >= 0 && xi < a.w && yi >= 0 && yi < a.h;
+          const bool in = c.valid && xi >= 0 && xi < a.w && yi >= 0 && yi < a.h;
           c.tw[2 * dy + dx] = in ? (dx ? ax : bx) * (dy ? ay : by) : 0.f;
           const int xc = min(max(xi, 0), a.w - 1), yc = min(max(yi, 0), a.h - 1);
-          const float4* tp = reinterpret_cast<const float4*>(base + ((long long)yc * a.w + xc) * kC);
-          c.tf[2 * (2 * dy + dx)] = __ldg(tp);
-          c.tf[2 * (2 * dy + dx) + 1] = __ldg(tp + 1);
+          c.tf[2 * dy + dx] = __ldg(reinterpret_cast<const uint4*>(base + ((long long)yc * a.w + xc) * kC));
         }
     }
     if (want_rgb) {
@@ -217,19 +210,16 @@ struct QuadOps {
       const float x0f = floorf(fx), y0f = floorf(fy);
       const int x0 = (int)x0f, y0 = (int)y0f;
       const float ax = fx - x0f, ay = fy - y0f, bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
-      const float* base = a.rgbs + (long long)v * a.H * a.W * 3;
+      const float* base = a.rgba + (long long)vc * a.H * a.W * 4;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
           const int xi = x0 + dx, yi = y0 + dy;
-          const bool in = xi >= 0 && xi < a.W && yi >= 0 && yi < a.H;
+          const bool in = c.valid && xi >= 0 && xi < a.W && yi >= 0 && yi < a.H;
           c.twr[2 * dy + dx] = in ? (dx ? ax : bx) * (dy ? ay : by) : 0.f;
           const int xc = min(max(xi, 0), a.W - 1), yc = min(max(yi, 0), a.H - 1);
-          const float* tp = base + ((long long)yc * a.W + xc) * 3;
-          c.tr[3 * (2 * dy + dx)] = __ldg(tp);
-          c.tr[3 * (2 * dy + dx) + 1] = __ldg(tp + 1);
-          c.tr[3 * (2 * dy + dx) + 2] = __ldg(tp + 2);
+          c.tr[2 * dy + dx] = __ldg(reinterpret_cast<const float4*>(base + ((long long)yc * a.W + xc) * 4));
         }
     }
   }
@@ -242,17 +232,19 @@ struct QuadOps {
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const float wgt = c.tw[t];
-      c.ch[0] += c.tf[2 * t].x * wgt; c.ch[1] += c.tf[2 * t].y * wgt;
-      c.ch[2] += c.tf[2 * t].z * wgt; c.ch[3] += c.tf[2 * t].w * wgt;
-      c.ch[4] += c.tf[2 * t + 1].x * wgt; c.ch[5] += c.tf[2 * t + 1].y * wgt;
-      c.ch[6] += c.tf[2 * t + 1].z * wgt; c.ch[7] += c.tf[2 * t + 1].w * wgt;
+      const uint32_t u[4] = {c.tf[t].x, c.tf[t].y, c.tf[t].z, c.tf[t].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c.ch[2 * j] += __uint_as_float(u[j] << 16) * wgt;
+        c.ch[2 * j + 1] += __uint_as_float(u[j] & 0xffff0000u) * wgt;
+      }
     }
     float rgb[3] = {0.f, 0.f, 0.f};
     if (want_rgb) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float wgt = c.twr[t];
-        rgb[0] += c.tr[3 * t] * wgt; rgb[1] += c.tr[3 * t + 1] * wgt; rgb[2] += c.tr[3 * t + 2] * wgt;
+        rgb[0] += c.tr[t].x * wgt; rgb[1] += c.tr[t].y * wgt; rgb[2] += c.tr[t].z * wgt;
       }
     }
     c.mask = c.mask_proj;

@@ -16,12 +16,18 @@
 // gathered / pooled channels, and the twins exchange only two scalars per row and iteration (the
 // partial visibility logits).
 //
-// Default NT = 1: TWO independent CTAs per SM, each with one 128-row tile:
+// TWO independent CTAs per SM, each with one 128-row tile:
 //   warps 0-3 : twin 0 (quadrant = w & 3)      warps 4-7 : twin 1 of the same rows
 //   warp 8    : MMA issuer (one elected lane)  warp 9    : weight producer
-// NT = 2 (DYN_VIEW_TILES=2, kept for comparison): one 576-thread CTA per SM with two tiles in a
-// ping-pong schedule (warps 0-7 / 8-15 twins, 16 issuer, 17 producer); measured 5 % slower because the
-// two tiles run in lock step behind the in-order issuer (profiles/r01_kernels.md).
+// (the NT = 2 template value -- one 576-thread CTA with two ping-pong tiles -- was measured 5 % slower in
+// round 1 and is no longer instantiated; the alternating two-tile schedule lives in view_quad.cu).
+//
+// Latency hiding inside a CTA (round 2, profiles/r02_view_kernels.md): the source views are read in
+// their packed per-frame layouts (bf16 channels-last features: 2 x 16-byte loads per tap and twin; RGBA
+// fp32 images: 1 load per tap), the taps are ISSUED right after the projection and consumed after the
+// positional-encoding operand has been built and handed to the tensor cores, the per-ray reference
+// feature is loaded before the wait for ray_dir_fc.2, the next iteration's points before the last wait,
+// and the camera matrices sit in shared memory (lanes of a warp index different views).
 #include <cstdlib>
 #include "fused_engine.cuh"
 #include "geometry.cuh"
@@ -36,8 +42,9 @@ namespace {
 
 constexpr bool kTwinPP = true;  // ping-pong (measured 8% faster than lock-step, profiles/r01_kernels.md)
 constexpr int kTwinATile = 65536;  // K <= 256 in the per-view nets: 32 k-groups
-constexpr int T_B1 = 0, T_B2 = 256, T_B3 = 304, T_B4 = 560, T_B5 = 688, T_B6 = 816, T_W6V = 944,
-              T_B7 = 1072, T_W8 = 1200, T_MISC = 1328, T_DFEAT = 1344, T_XCH = 1408;  // + 2 x 256 exchange
+constexpr int T_B2 = 0, T_B4 = 48, T_B5 = 176, T_B6 = 304, T_W6V = 432, T_B7 = 560, T_W8 = 688,
+              T_MISC = 816, T_DFEAT = 832, T_CAMS = 880 /* 16 views x (P 12 + centre 3 + pad) */,
+              T_XCH = T_CAMS + 256;  // + 2 x [2][256] exchange
 constexpr int kTwinConst = T_XCH + 1024;
 // NT = 128-row tiles per CTA: 2 -> one 576-thread CTA per SM (ping-pong between its tiles);
 // 1 -> two independent 320-thread CTAs per SM, each with one tile and a 2-slot weight ring, so
@@ -115,9 +122,9 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
   if (tid == 0) init_barriers(bar0, PP, /*arrivals=*/NT == 2 ? 256 : 128, RING);
   {
     const float* prm = a.params;
-    for (int i = tid; i < 256; i += blockDim.x) {
-      if (ST) cst[T_B1 + i] = prm[a.o_b1 + i];
-      cst[T_B3 + i] = prm[a.o_b3 + i];
+    for (int i = tid; i < 256; i += blockDim.x) {  // camera matrices: lanes index them by view
+      const int vv = i >> 4, j = i & 15;
+      cst[T_CAMS + i] = j < 12 ? a.cams.P[vv][j] : (j < 15 ? a.cams.center[vv][j - 12] : 0.f);
     }
     for (int i = tid; i < 128; i += blockDim.x) {
       cst[T_B4 + i] = prm[a.o_b4 + i];
@@ -172,6 +179,21 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
     constexpr int NG = ST ? 5 : (0);  // static: 5 channel groups per twin (set below for dynamic)
     (void)NG;
 
+    // the first point of this thread; later ones are fetched one iteration ahead (before the last MMA wait)
+    float np3[3], nq3[3];
+    auto fetch_point = [&](int it2) {
+      const long long pl2 = ((long long)it2 * ROWS + t) / VP;
+      np3[0] = 0.f; np3[1] = 0.f; np3[2] = 0.f;
+      if (pl2 < a.P) { np3[0] = a.pts[pl2 * 3]; np3[1] = a.pts[pl2 * 3 + 1]; np3[2] = a.pts[pl2 * 3 + 2]; }
+      nq3[0] = np3[0]; nq3[1] = np3[1]; nq3[2] = np3[2];
+      if (!ST && pl2 < a.P && v < a.V) {
+        const float* q = a.pts_seq + ((long long)v * a.seq_stride + pl2) * 3;
+        nq3[0] = q[0]; nq3[1] = q[1]; nq3[2] = q[2];
+      }
+    };
+    if ((int)blockIdx.x < n_iter) fetch_point((int)blockIdx.x);
+    const bool want_rgb = (tw == 0) || (ST && a.mask_rgb);
+
     for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
       const long long pl = ((long long)it * ROWS + t) / VP;
       const bool pt_ok = pl < a.P;
@@ -181,25 +203,68 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
 
       TS();  // 0: iteration start
       // ---- geometry (both twins; cheap) ----
-      float p3[3] = {0.f, 0.f, 0.f}, q3[3];
-      if (pt_ok) { p3[0] = a.pts[pl * 3]; p3[1] = a.pts[pl * 3 + 1]; p3[2] = a.pts[pl * 3 + 2]; }
-      q3[0] = p3[0]; q3[1] = p3[1]; q3[2] = p3[2];
-      if (!ST && valid) {
-        const float* q = a.pts_seq + ((long long)v * a.seq_stride + pl) * 3;
-        q3[0] = q[0]; q3[1] = q[1]; q3[2] = q[2];
-      }
+      const float p3[3] = {np3[0], np3[1], np3[2]}, q3[3] = {nq3[0], nq3[1], nq3[2]};
       const int vc = valid ? v : 0;
+      const float* cam = cst + T_CAMS + 16 * vc;  // P (12) | centre (3)
       float pu, pv;
       bool front;
-      project_point(a.cams.P[vc], q3[0], q3[1], q3[2], pu, pv, front);
+      project_point(cam, q3[0], q3[1], q3[2], pu, pv, front);
       const bool inb = (pu <= wh - 1.f) && (pu >= 0.f) && (pv <= hh - 1.f) && (pv >= 0.f);
       const float mask_proj = (valid && inb && front) ? 1.f : 0.f;
+
+      // ---- issue the bilinear taps now: 2 x 16 B per tap of this twin's 16 bf16 feature channels
+      //      (+ 1 x 16 B RGBA); they are consumed after the ray_dir_fc.0 operand has been built ----
+      uint4 tf[8];
+      float4 tr[4];
+      float tw4[4], twr[4];
+      {
+        const float gx = 2.f * pu / (wh - 1.f) - 1.f, gy = 2.f * pv / (hh - 1.f) - 1.f;
+        const bool ld = valid && !(a.ablate & 1);
+        {
+          const float fx = (gx + 1.f) * 0.5f * (float)(a.w - 1), fy = (gy + 1.f) * 0.5f * (float)(a.h - 1);
+          const float x0f = floorf(fx), y0f = floorf(fy);
+          const int x0 = (int)x0f, y0 = (int)y0f;
+          const float ax = fx - x0f, ay = fy - y0f, bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
+          const uint16_t* base = a.feat_bf + (long long)vc * a.h * a.w * kC + 16 * tw;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              // out-of-range taps (and padding rows) load a clamped texel with weight 0: no branch, all loads
+              // of this thread are in flight together
+              const int xi = x0 + dx, yi = y0 + dy;
+              const bool in = ld && xi >= 0 && xi < a.w && yi >= 0 && yi < a.h;
+              tw4[2 * dy + dx] = in ? (dx ? ax : bx) * (dy ? ay : by) : 0.f;
+              const int xc = min(max(xi, 0), a.w - 1), yc = min(max(yi, 0), a.h - 1);
+              const uint4* tp = reinterpret_cast<const uint4*>(base + ((long long)yc * a.w + xc) * kC);
+              tf[2 * (2 * dy + dx)] = __ldg(tp);
+              tf[2 * (2 * dy + dx) + 1] = __ldg(tp + 1);
+            }
+        }
+        if (want_rgb) {
+          const float fx = (gx + 1.f) * 0.5f * (float)(a.W - 1), fy = (gy + 1.f) * 0.5f * (float)(a.H - 1);
+          const float x0f = floorf(fx), y0f = floorf(fy);
+          const int x0 = (int)x0f, y0 = (int)y0f;
+          const float ax = fx - x0f, ay = fy - y0f, bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
+          const float* base = a.rgba + (long long)vc * a.H * a.W * 4;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const int xi = x0 + dx, yi = y0 + dy;
+              const bool in = ld && xi >= 0 && xi < a.W && yi >= 0 && yi < a.H;
+              twr[2 * dy + dx] = in ? (dx ? ax : bx) * (dy ? ay : by) : 0.f;
+              const int xc = min(max(xi, 0), a.W - 1), yc = min(max(yi, 0), a.H - 1);
+              tr[2 * dy + dx] = __ldg(reinterpret_cast<const float4*>(base + ((long long)yc * a.W + xc) * 4));
+            }
+        }
+      }
+
       float rd[4];
       {
         float a0 = a.cams.tgt[0] - p3[0], a1 = a.cams.tgt[1] - p3[1], a2 = a.cams.tgt[2] - p3[2];
         normalize3(a0, a1, a2);
-        float b0 = a.cams.center[vc][0] - q3[0], b1 = a.cams.center[vc][1] - q3[1],
-              b2 = a.cams.center[vc][2] - q3[2];
+        float b0 = cam[12] - q3[0], b1 = cam[13] - q3[1], b2 = cam[14] - q3[2];
         normalize3(b0, b1, b2);
         rd[0] = a0 - b0; rd[1] = a1 - b1; rd[2] = a2 - b2;
         rd[3] = a0 * b0 + a1 * b1 + a2 * b2;
@@ -207,10 +272,13 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       }
 
       if (ST) {
-        // ---- layer-1 operand, 56 columns per twin (component-major PE, see view_twin_build) ----
+        // ---- layer-1 operand, 56 columns per twin (component-major PE, see view_twin_build); each
+        //      8-column group is stored as soon as it is complete (short register live ranges while the
+        //      taps are in flight).  Padding rows keep (finite) garbage: every use of their layer outputs
+        //      is guarded by `valid` ----
         float pl6[6];
         {
-          const float ox = a.cams.center[vc][0], oy = a.cams.center[vc][1], oz = a.cams.center[vc][2];
+          const float ox = cam[12], oy = cam[13], oz = cam[14];
           float dx = p3[0] - ox, dy = p3[1] - oy, dz = p3[2] - oz;
           normalize3(dx, dy, dz);
           pl6[0] = dx; pl6[1] = dy; pl6[2] = dz;
@@ -220,85 +288,60 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         }
         float xin[56];
         if (tw == 0) {
-          pe_comp(p3[0], xin); pe_comp(p3[1], xin + 11); pe_comp(p3[2], xin + 22);
-          pe_comp(pl6[0], xin + 33); pe_comp(pl6[1], xin + 44);
-          xin[55] = 0.f;
+          pe_comp(p3[0], xin);         store8(arow, 0, xin);
+          pe_comp(p3[1], xin + 11);    store8(arow, 8, xin + 8);
+          pe_comp(p3[2], xin + 22);    store8(arow, 16, xin + 16); store8(arow, 24, xin + 24);
+          pe_comp(pl6[0], xin + 33);   store8(arow, 32, xin + 32);
+          pe_comp(pl6[1], xin + 44);   xin[55] = 0.f;
+          store8(arow, 40, xin + 40);  store8(arow, 48, xin + 48);
         } else {
-          pe_comp(pl6[2], xin); pe_comp(pl6[3], xin + 11); pe_comp(pl6[4], xin + 22);
-          pe_comp(pl6[5], xin + 33);
+          pe_comp(pl6[2], xin);        store8(arow, 56, xin);
+          pe_comp(pl6[3], xin + 11);   store8(arow, 64, xin + 8);
+          pe_comp(pl6[4], xin + 22);   store8(arow, 72, xin + 16); store8(arow, 80, xin + 24);
+          pe_comp(pl6[5], xin + 33);   store8(arow, 88, xin + 32);
           xin[44] = rd[0]; xin[45] = rd[1]; xin[46] = rd[2]; xin[47] = rd[3];
           xin[48] = 1.f; xin[49] = 1.f;  // bias columns of ray_dir_fc.0 (hi, lo)
 #pragma unroll
           for (int i = 50; i < 56; ++i) xin[i] = 0.f;
+          store8(arow, 96, xin + 40);  store8(arow, 104, xin + 48);
         }
-        if (!valid) {
-#pragma unroll
-          for (int i = 0; i < 56; ++i) xin[i] = 0.f;
-        }
-#pragma unroll
-        for (int g = 0; g < 7; ++g) store8(arow, 56 * tw + 8 * g, xin + 8 * g);
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(bar_aready(bar0, bt, RING));
       }
 
       TS();  // 1: after F1 operand + arrive
-      // ---- gather: rgb (both twins) + this twin's 16 feature channels ----
+      // ---- consume the taps: rgb (twin 0, or both when mask_rgb) + this twin's 16 feature channels ----
       float chv[40];  // this twin's pooled channels (layout in view_twin_build)
 #pragma unroll
       for (int i = 0; i < 40; ++i) chv[i] = 0.f;
       float rgb[3] = {0.f, 0.f, 0.f};
-      if (valid && !(a.ablate & 1)) {
-        const float gx = 2.f * pu / (wh - 1.f) - 1.f, gy = 2.f * pv / (hh - 1.f) - 1.f;
-        {
-          const float fx = (gx + 1.f) * 0.5f * (float)(a.w - 1), fy = (gy + 1.f) * 0.5f * (float)(a.h - 1);
-          const float x0f = floorf(fx), y0f = floorf(fy);
-          const int x0 = (int)x0f, y0 = (int)y0f;
-          const float ax = fx - x0f, ay = fy - y0f, bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
-          const float* base = a.feat_cl + (long long)v * a.h * a.w * kC + 16 * tw;
-          const int fo = tw == 0 ? 3 : 0;  // twin 0 keeps rgb in slots 0..2
+      {
+        const int fo = tw == 0 ? 3 : 0;  // twin 0 keeps rgb in slots 0..2
 #pragma unroll
-          for (int dy = 0; dy < 2; ++dy)
+        for (int tp = 0; tp < 4; ++tp) {
+          const float wgt = tw4[tp];
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-              // out-of-range taps load a clamped texel with weight 0: no branch, so all 16
-              // tap loads of this thread are in flight together
-              const int xi = x0 + dx, yi = y0 + dy;
-              const bool in = xi >= 0 && xi < a.w && yi >= 0 && yi < a.h;
-              const float wgt = in ? (dx ? ax : bx) * (dy ? ay : by) : 0.f;
-              const int xc = min(max(xi, 0), a.w - 1), yc = min(max(yi, 0), a.h - 1);
-              const float4* tp = reinterpret_cast<const float4*>(base + ((long long)yc * a.w + xc) * kC);
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const uint4 q = tf[2 * tp + hlf];
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 q = __ldg(tp + j);
-                if (tw == 0) {
-                  chv[3 + 4 * j] += q.x * wgt; chv[4 + 4 * j] += q.y * wgt;
-                  chv[5 + 4 * j] += q.z * wgt; chv[6 + 4 * j] += q.w * wgt;
-                } else {
-                  chv[4 * j] += q.x * wgt; chv[1 + 4 * j] += q.y * wgt;
-                  chv[2 + 4 * j] += q.z * wgt; chv[3 + 4 * j] += q.w * wgt;
-                }
+            for (int j = 0; j < 4; ++j) {
+              const float lo = __uint_as_float(u[j] << 16), hi = __uint_as_float(u[j] & 0xffff0000u);
+              if (tw == 0) {
+                chv[3 + 8 * hlf + 2 * j] += lo * wgt; chv[3 + 8 * hlf + 2 * j + 1] += hi * wgt;
+              } else {
+                chv[8 * hlf + 2 * j] += lo * wgt; chv[8 * hlf + 2 * j + 1] += hi * wgt;
               }
             }
-          (void)fo;
+          }
         }
-        {
-          const float fx = (gx + 1.f) * 0.5f * (float)(a.W - 1), fy = (gy + 1.f) * 0.5f * (float)(a.H - 1);
-          const float x0f = floorf(fx), y0f = floorf(fy);
-          const int x0 = (int)x0f, y0 = (int)y0f;
-          const float ax = fx - x0f, ay = fy - y0f, bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
-          const float* base = a.rgbs + (long long)v * a.H * a.W * 3;
+        (void)fo;
+        if (want_rgb) {
 #pragma unroll
-          for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-              const int xi = x0 + dx, yi = y0 + dy;
-              const bool in = xi >= 0 && xi < a.W && yi >= 0 && yi < a.H;
-              const float wgt = in ? (dx ? ax : bx) * (dy ? ay : by) : 0.f;
-              const int xc = min(max(xi, 0), a.W - 1), yc = min(max(yi, 0), a.H - 1);
-              const float* tp = base + ((long long)yc * a.W + xc) * 3;
-              rgb[0] += __ldg(tp) * wgt; rgb[1] += __ldg(tp + 1) * wgt; rgb[2] += __ldg(tp + 2) * wgt;
-            }
+          for (int tp = 0; tp < 4; ++tp) {
+            rgb[0] += tr[tp].x * twr[tp]; rgb[1] += tr[tp].y * twr[tp]; rgb[2] += tr[tp].z * twr[tp];
+          }
         }
       }
       float mask = mask_proj;
@@ -326,7 +369,14 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         tc_fence_before_sync();
         mbar_arrive(bar_aready(bar0, bt, RING));
         TS();  // 4: F1 epilogue done
-        // ---- F2: src_feat (35 of 48 columns) * ref_feat; twin 0 keeps 0..17, twin 1 keeps 18..34 ----
+        // ---- F2: src_feat (35 of 48 columns) * ref_feat; twin 0 keeps 0..17, twin 1 keeps 18..34.
+        //      The per-ray reference feature is loaded BEFORE the wait (its L2 latency hides behind the MMA) ----
+        float rfv[18];
+        {
+          const float* rf = a.ref_feat + ray * kF + 18 * tw;
+#pragma unroll
+          for (int i = 0; i < 18; ++i) rfv[i] = (tw == 0 || i < 17) ? __ldg(rf + i) : 0.f;
+        }
         mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
         TS();  // 5: F2 acc ready
         tc_fence_after_sync();
@@ -334,14 +384,13 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         tmem_ld32(tacc, s48);
         tmem_ld16(tacc + 32, s48 + 32);
         tmem_wait_ld();
-        const float* rf = a.ref_feat + ray * kF;
         if (tw == 0) {
 #pragma unroll
-          for (int i = 0; i < 18; ++i) chv[19 + i] = valid ? (s48[i] + cst[T_B2 + i]) * __ldg(rf + i) : 0.f;
+          for (int i = 0; i < 18; ++i) chv[19 + i] = valid ? (s48[i] + cst[T_B2 + i]) * rfv[i] : 0.f;
         } else {
 #pragma unroll
           for (int i = 0; i < 17; ++i)
-            chv[16 + i] = valid ? (s48[18 + i] + cst[T_B2 + 18 + i]) * __ldg(rf + 18 + i) : 0.f;
+            chv[16 + i] = valid ? (s48[18 + i] + cst[T_B2 + 18 + i]) * rfv[i] : 0.f;
         }
       } else {
         // dynamic: + time feature on this twin's channels (mlp_network.py:244-247)
@@ -494,6 +543,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       mbar_arrive(bar_aready(bar0, bt, RING));
 
       TS();  // 14: F6 epilogue done
+      if (it + (int)gridDim.x < n_iter) fetch_point(it + (int)gridDim.x);  // next iteration's point
       // ---- F7: vis2 = sigmoid(vis_fc2.2 . ELU(vis_fc2.0)) * mask ----
       mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
       TS();  // 15: F7 acc ready
@@ -693,9 +743,7 @@ int launch_view_twin(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st)
   DYN_CUDA(cudaGetDevice(&dev));
   DYN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int VP = V <= 8 ? 8 : 16;
-  // DYN_VIEW_TILES=2 selects the one-CTA-per-SM ping-pong variant (kept for comparison)
-  const char* e_nt = getenv("DYN_VIEW_TILES");
-  const int nt = (e_nt && e_nt[0] == '2') ? 2 : 1;
+  const int nt = 1;
   const long long rows = 128LL * nt;
   const long long n_iter = (a.P * VP + rows - 1) / rows;
   const long long slots = (long long)sms * (nt == 1 ? 2 : 1);
@@ -709,7 +757,7 @@ int launch_view_twin(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st)
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, twin_smem(NTV))); \
     view_twin_kernel<VPV, STV, NTV><<<grid, NTV * 256 + 64, twin_smem(NTV), st>>>(a);            \
   } while (0)
-#define LAUNCH_VT2(VPV, STV) do { if (nt == 1) LAUNCH_VT(VPV, STV, 1); else LAUNCH_VT(VPV, STV, 2); } while (0)
+#define LAUNCH_VT2(VPV, STV) LAUNCH_VT(VPV, STV, 1)
   if (st_net) { if (VP == 8) LAUNCH_VT2(8, true); else LAUNCH_VT2(16, true); }
   else { if (VP == 8) LAUNCH_VT2(8, false); else LAUNCH_VT2(16, false); }
 #undef LAUNCH_VT2

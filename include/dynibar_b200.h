@@ -171,25 +171,30 @@ int dyn_net_static(dyn_net_t net, const float* pts, const float* ref_rays,
 /* ---- fused a4-a11 (DYN_PREC_BF16): Projector.compute_with_motions fused INTO
  * the network evaluation -- the [R,S,V,35] gather output never reaches HBM.
  * Replaces the call pairs at render_ray.py:503-521 + :538-564 (== :715-774,
- * :998-1059).  feat_cl is the CHANNELS-LAST copy [V,h,w,C] of the feature maps
- * (dyn_featmaps_channels_last, once per frame).  mask_out [R,S,V] receives the
- * projector mask (needed by dyn_composite).  V <= 16.
+ * :998-1059).  The source views arrive in two packed per-frame layouts (pack them ONCE per frame):
+ *   feat_cl  = channels-last bf16 copy [V,h,w,C] of the feature maps (dyn_featmaps_channels_last):
+ *              one bilinear tap of all C = 32 channels is 64 contiguous bytes;
+ *   src_rgba = the source images [V,H,W,3] padded to [V,H,W,4] fp32 (dyn_rgbs_rgba): one tap is
+ *              one aligned 16-byte load.
+ * mask_out [R,S,V] receives the projector mask (needed by dyn_composite).  V <= 16.
  * static:  needs ray_o, ray_d [R,3] (Plucker coordinates are formed inside).
  * dynamic: pts_seq [V,R,S,3] displaced points, ray_dir [R,3] normalised. */
 size_t dyn_net_fused_workspace_bytes(int kind, int R, int S, int V);
-int dyn_featmaps_channels_last(const float* featmaps, float* out, int V, int C,
+int dyn_featmaps_channels_last(const float* featmaps, void* out_bf16, int V, int C,
                                int h, int w, void* stream);
+int dyn_rgbs_rgba(const float* src_rgbs, float* out_rgba, int V, int H, int W,
+                  void* stream);
 int dyn_net_static_fused(dyn_net_t net, const float* pts, const float* ray_o,
                          const float* ray_d, const float* query_cam,
-                         const float* src_rgbs, const float* src_cams,
-                         const float* feat_cl, int R, int S, int V, int H,
+                         const float* src_rgba, const float* src_cams,
+                         const void* feat_cl, int R, int S, int V, int H,
                          int W, int C, int h, int w, float* raw,
                          float* mask_out, void* workspace,
                          size_t workspace_bytes, void* stream);
 int dyn_net_dynamic_fused(dyn_net_t net, const float* pts, const float* pts_seq,
                           const float* ray_dir, const float* query_cam,
-                          const float* src_rgbs, const float* src_cams,
-                          const float* feat_cl, float time, int R, int S, int V,
+                          const float* src_rgba, const float* src_cams,
+                          const void* feat_cl, float time, int R, int S, int V,
                           int H, int W, int C, int h, int w, float* raw,
                           float* mask_out, void* workspace,
                           size_t workspace_bytes, void* stream);
@@ -258,10 +263,11 @@ int dyn_debug_pack_layer(const float* W, const float* bias, int N, int Kw, int N
  * 128-row tile: the layout activations use between the fused kernels. */
 size_t dyn_debug_tile_image_off(long long row, int kgroup, int kgroups);
 
-/* comparison hook: 0 (default) runs the fused per-view stage with the quad-schedule kernel
- * (csrc/view_quad.cu), 1 with the twin-warp kernel of round 1 (csrc/view_twin.cu); the environment
- * variable DYN_VIEW_KERNEL=twin sets the initial value. */
-void dyn_debug_set_view_kernel(int twin);
+/* comparison hook: 0 (default) runs the fused per-view stage with the twin-warp kernel
+ * (csrc/view_twin.cu: two independent CTAs per SM), 1 with the quad-schedule kernel
+ * (csrc/view_quad.cu: one CTA per SM alternating between two tiles); the environment variable
+ * DYN_VIEW_KERNEL=quad sets the initial value. */
+void dyn_debug_set_view_kernel(int quad);
 
 /* profiling hook: when set, block 0 of the fused static per-view kernel writes clock64()
  * phase timestamps ([2 twins][64]) into dev_buf (profiles/scripts/prof_phases.py). */

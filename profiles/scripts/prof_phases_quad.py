@@ -24,6 +24,7 @@ def main():
   kind = sys.argv[1] if len(sys.argv) > 1 else "static"
   DEV = "cuda:0"
   rr.set_precision("bf16")
+  _lib.lib.dyn_debug_set_view_kernel(1)  # quad kernel
   R, S = 8192, 128
   batch, feat_c, feat_f, frame, t, offs = synthetic.make_scene(rays=R, seed=0)
   model, args = synthetic.make_model(64, 64)

@@ -7,28 +7,32 @@
 #include "tc.cuh"
 using namespace dyn::tc;
 
-__global__ void __launch_bounds__(64) rate_kernel(const uint8_t* src, int src_chunks, int slots, int chunk_bytes,
-                                                  int n_copies, long long* out) {
+// `nprod` producer threads (lane 0 of warps 0 .. nprod-1), each with its own `slots` ring slots
+__global__ void __launch_bounds__(128) rate_kernel(const uint8_t* src, int src_chunks, int slots, int chunk_bytes,
+                                                   int n_copies, long long* out, int nprod) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[16];
+  __shared__ uint64_t bars[32];
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int i = 0; i < slots; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int i = 0; i < slots * nprod; ++i) mbar_init(smem_u32(&bars[i]), 1);
     mbar_fence_init();
   }
   __syncthreads();
-  if (tid == 0) {
+  if ((tid & 31) == 0 && (tid >> 5) < nprod) {
+    const int p = tid >> 5;
+    uint64_t* mybars = bars + p * slots;
+    uint8_t* mysmem = smem + (size_t)p * slots * chunk_bytes;
     long long t0 = clock64();
     for (int c = 0; c < n_copies + slots; ++c) {
       const int s = c % slots;
-      if (c >= slots) mbar_wait(smem_u32(&bars[s]), ((c / slots) - 1) & 1);  // copy c - slots has landed
+      if (c >= slots) mbar_wait(smem_u32(&mybars[s]), ((c / slots) - 1) & 1);  // copy c - slots has landed
       if (c < n_copies) {
-        mbar_arrive_expect_tx(smem_u32(&bars[s]), chunk_bytes);
-        bulk_g2s(smem_u32(smem + (size_t)s * chunk_bytes), src + (size_t)((c + blockIdx.x) % src_chunks) * chunk_bytes,
-                 chunk_bytes, smem_u32(&bars[s]));
+        mbar_arrive_expect_tx(smem_u32(&mybars[s]), chunk_bytes);
+        bulk_g2s(smem_u32(mysmem + (size_t)s * chunk_bytes),
+                 src + (size_t)((c + blockIdx.x + 7 * p) % src_chunks) * chunk_bytes, chunk_bytes, smem_u32(&mybars[s]));
       }
     }
-    out[blockIdx.x] = clock64() - t0;
+    if (p == 0) out[blockIdx.x] = clock64() - t0;
   }
 }
 
@@ -43,7 +47,7 @@ int main() {
       if (cps == 2 && slots > 6) continue;
       const int grid = 148 * cps;
       const int smem = cps == 2 ? 6 * chunk : 8 * chunk;  // pins the CTAs-per-SM count
-      for (int rep = 0; rep < 2; ++rep) rate_kernel<<<grid, 64, smem>>>(src, src_chunks, slots, chunk, n, out);
+      for (int rep = 0; rep < 2; ++rep) rate_kernel<<<grid, 128, smem>>>(src, src_chunks, slots, chunk, n, out, 1);
       cudaError_t e = cudaDeviceSynchronize();
       long long h[296]; cudaMemcpy(h, out, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
       double s = 0; for (int i = 0; i < grid; ++i) s += h[i];
@@ -52,5 +56,19 @@ int main() {
              cps, slots, (double)n * chunk / cyc, (double)n * chunk / cyc * cps, cyc / n * slots, cudaGetErrorString(e));
     }
   }
+  // one CTA per SM, several producer threads (different warps), 2-4 copies in flight each
+  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * chunk);
+  for (int nprod : {1, 2, 3, 4}) {
+    for (int slots : {2, 3}) {
+      for (int rep = 0; rep < 2; ++rep) rate_kernel<<<148, 128, 12 * chunk>>>(src, src_chunks, slots, chunk, n, out, nprod);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long h[148]; cudaMemcpy(h, out, sizeof(long long) * 148, cudaMemcpyDeviceToHost);
+      double s = 0; for (int i = 0; i < 148; ++i) s += h[i];
+      const double cyc = s / 148;
+      printf("1 CTA/SM, %d producer threads x %d copies in flight: %6.1f B/clk per SM  %s\n", nprod, slots,
+             (double)n * chunk * nprod / cyc, cudaGetErrorString(e));
+    }
+  }
+  // smaller copies from one producer: 8 x 2 KB pieces per 16 KB stage (same bytes, more requests)
   return 0;
 }

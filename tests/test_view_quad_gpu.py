@@ -30,7 +30,7 @@ def _inputs(V_dy, V_st, rays, S, seed, stress=False, mask_rgb=0):
 
 def _run(b, fc, m, pts, seq, tt, twin):
   from dynibar_b200 import render_ray as rr
-  _lib.lib.dyn_debug_set_view_kernel(1 if twin else 0)
+  _lib.lib.dyn_debug_set_view_kernel(0 if twin else 1)
   try:
     ray_dir = torch.nn.functional.normalize(b["ray_d"], dim=-1)
     raw_st, m_st = rr.net_static_fused(m.net_coarse_st, pts, b["ray_o"], b["ray_d"], b["camera"],
