@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(320, 1) motion_fused_kernel(const __grid_const
   const int n_iter = (int)((a.N + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) < a.producers) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0, tid & 31, a.producers);
   } else if (warp == 8) {
     issuer_loop<kPP>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(320, 1) point1_fused_kernel(const __grid_const
   const int n_iter = (int)((a.P + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) < a.producers) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0, tid & 31, a.producers);
   } else if (warp == 8) {
     issuer_loop<kPP>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(320, 1) point2_fused_kernel(const __grid_const
   const int n_iter = (int)((a.P + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) < a.producers) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0, tid & 31, a.producers);
   } else if (warp == 8) {
     issuer_loop<kPP>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(320, 1) rgbhead_fused_kernel(const __grid_cons
   const int n_iter = (int)((a.P * VP + 255) / 256);
 
   if (warp == 9) {
-    if ((tid & 31) == 0) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) < a.producers) producer_loop<kPP>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0, tid & 31, a.producers);
   } else if (warp == 8) {
     issuer_loop<kPP>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base);
   } else {
@@ -748,6 +748,7 @@ int fused_chain_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_byte
 }
 
 int launch_motion_fused(const dyn_net* n, MotionFusedArgs& a, cudaStream_t st) {
+  a.producers = producer_lanes();
   if (!n->chain[0].img) return fail(DYN_E_INVALID, "motion net has no fused images");
   a.wimg = n->chain[0].img; a.chunks = n->chain[0].tab; a.nchunks = n->chain[0].nchunks;
   a.params = n->params;
@@ -759,6 +760,7 @@ int launch_motion_fused(const dyn_net* n, MotionFusedArgs& a, cudaStream_t st) {
 }
 
 int launch_point1_fused(const dyn_net* n, Point1Args& a, cudaStream_t st) {
+  a.producers = producer_lanes();
   if (!n->chain[0].img) return fail(DYN_E_INVALID, "net has no fused point-stage images");
   const bool dynamic = n->kind == DYN_NET_DYNAMIC;
   a.wimg = n->chain[0].img; a.chunks = n->chain[0].tab; a.nchunks = n->chain[0].nchunks;
@@ -770,6 +772,7 @@ int launch_point1_fused(const dyn_net* n, Point1Args& a, cudaStream_t st) {
 }
 
 int launch_point2_fused(const dyn_net* n, Point2Args& a, cudaStream_t st) {
+  a.producers = producer_lanes();
   if (!n->chain[1].img) return fail(DYN_E_INVALID, "net has no fused point-stage images");
   const bool dynamic = n->kind == DYN_NET_DYNAMIC;
   a.wimg = n->chain[1].img; a.chunks = n->chain[1].tab; a.nchunks = n->chain[1].nchunks;
@@ -791,6 +794,7 @@ int launch_point2_fused(const dyn_net* n, Point2Args& a, cudaStream_t st) {
 }
 
 int launch_rgbhead_fused(const dyn_net* n, RgbHeadArgs& a, cudaStream_t st) {
+  a.producers = producer_lanes();
   if (!n->chain[2].img) return fail(DYN_E_INVALID, "static net has no fused blending-head images");
   a.wimg = n->chain[2].img; a.chunks = n->chain[2].tab; a.nchunks = n->chain[2].nchunks;
   a.params = n->params;

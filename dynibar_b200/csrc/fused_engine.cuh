@@ -35,6 +35,11 @@ __device__ __forceinline__ float elu_log2(float x2) {
   const float e = ex2f(x2);
   return x2 > 0.f ? x2 : fmaf(e, 1.4426950408889634f, -1.4426950408889634f);
 }
+// ELU in true units from an accumulator on the exp2 scale (x2 = log2(e) * x): 4 instructions
+__device__ __forceinline__ float elu_from_log2(float x2) {
+  const float e = ex2f(x2);
+  return x2 > 0.f ? x2 * 0.6931471805599453f : e - 1.f;
+}
 __device__ __forceinline__ float sigmoid_fast(float x) {
   return __frcp_rn(1.f + ex2f(-x * 1.4426950408889634f));
 }
@@ -171,9 +176,15 @@ __device__ __forceinline__ int round_end(const FusedChunk* __restrict__ chunks, 
   return c + 1 < nchunks ? c + 1 : nchunks;
 }
 
+// One thread sustains ~40 B/clk of cp.async.bulk traffic however many copies it keeps in flight, two
+// threads ~79 B/clk, three ~100 B/clk (profiles/scripts/tma_rate.cu, profiles/r02_view_kernels.md), while
+// a layer at the full MMA rate consumes 64 B/clk of weights: `nlanes` lanes of the producer warp share
+// the chunk stream round-robin (lane p issues the chunks with cnt % nlanes == p; RING % nlanes == 0, so
+// a lane always refills the same ring slots).
 template <bool PP, int RING = kRing, int STAGE = kStageBytes>
 __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chunks, int nchunks,
-                                              const void* wimg, int n_iter, uint8_t* ring, uint32_t bar0) {
+                                              const void* wimg, int n_iter, uint8_t* ring, uint32_t bar0,
+                                              uint32_t lane = 0, uint32_t nlanes = 1) {
   const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(wimg);
   uint32_t cnt = 0;
   for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
@@ -181,6 +192,7 @@ __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chu
       const int c1 = PP ? round_end(chunks, c0, nchunks) : nchunks;
       for (int rep = 0; rep < (PP ? 2 : 1); ++rep) {
         for (int c = c0; c < c1; ++c, ++cnt) {
+          if (cnt % nlanes != lane) continue;
           const uint32_t st = cnt % RING;
           if (cnt >= RING) mbar_wait(bar0 + 8u * (RING + st), ((cnt / RING) - 1) & 1);
           const FusedChunk ch = chunks[c];
@@ -282,6 +294,8 @@ struct HostLayer {
   // (log2 e for layers whose ELU is evaluated on the exp2 scale, ln 2 for their consumers)
   const float* bias = nullptr;
   float scale = 1.f;
+  float bias_scale = -1.f;  // < 0: same as `scale` (differs when the layer CONSUMES a log2-scaled operand
+                            // and PRODUCES an exp2-scale accumulator: weights x ln2 x log2e = 1, bias x log2e)
 };
 constexpr int kBiasHi = -2, kBiasLo = -3;
 inline float bf2f(uint16_t h) {
@@ -317,7 +331,7 @@ inline void append_layer(const HostLayer& L, std::vector<uint8_t>& img, std::vec
           if (col >= 0) {
             val = L.W[(size_t)n * L.Kw + col] * L.scale;
           } else if (L.bias != nullptr && (col == kBiasHi || col == kBiasLo)) {
-            const float b = L.bias[n] * L.scale, hi = bf2f(f2bf(b));
+            const float b = L.bias[n] * (L.bias_scale >= 0.f ? L.bias_scale : L.scale), hi = bf2f(f2bf(b));
             val = col == kBiasHi ? hi : b - hi;
           }
         }

@@ -25,9 +25,19 @@ static bool use_twin_kernel() {
   return g_view_kernel == 0;
 }
 
+int producer_lanes() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DYN_PRODUCERS");
+    v = (e != nullptr && e[0] == '2') ? 2 : 1;  // two lanes of ONE warp do not help (divergence): r02_view_kernels.md
+  }
+  return v;
+}
+
 int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st) {
   if (V > 16) return fail(DYN_E_INVALID, "fused per-view kernel supports V <= 16 (got %d)", V);
   a.params = n->params;
+  a.producers = producer_lanes();
   const bool st_net = n->kind == DYN_NET_STATIC;
   if (st_net) {
     const StaticLayout& L = n->sl;

@@ -47,6 +47,7 @@ struct ViewFusedArgs {
   float* vis2;       // static [P*V]
   float* ray_diff;   // static [P*V,4]
   float* rgb_in;     // static [P*V,3] gathered source colours
+  int producers;     // lanes of the producer warp that stream weight chunks (1 or 2)
   int ablate;        // profiling only (DYN_ABLATE): 1 skip gather loads, 2 skip X/vis/mask stores, 4 skip pooled-output stores, 8 skip second pooling
   long long* dbg;    // optional: clock64() phase timestamps of block 0 (profiling builds/tests only)
 };
@@ -65,6 +66,7 @@ struct MotionFusedArgs {
   const void* wimg;
   const FusedChunk* chunks;
   int nchunks;
+  int producers;  // lanes of the producer warp that stream weight chunks
 };
 
 struct Point1Args {
@@ -79,6 +81,7 @@ struct Point1Args {
   const void* wimg;
   const FusedChunk* chunks;
   int nchunks;
+  int producers;  // lanes of the producer warp that stream weight chunks
 };
 
 struct Point2Args {
@@ -99,6 +102,7 @@ struct Point2Args {
   const void* wimg;
   const FusedChunk* chunks;
   int nchunks;
+  int producers;  // lanes of the producer warp that stream weight chunks
 };
 
 struct RgbHeadArgs {
@@ -111,6 +115,7 @@ struct RgbHeadArgs {
   const void* wimg;
   const FusedChunk* chunks;
   int nchunks;
+  int producers;  // lanes of the producer warp that stream weight chunks
 };
 
 int debug_pack_layer(const float* W, const float* bias, int N, int Kw, int Npad, int Kpad, const int* colmap,
@@ -136,6 +141,7 @@ int view_quad_build(dyn_net* n, const float* host_params, void* dst_dev, size_t 
 int launch_view_quad(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st);
 
 void set_view_kernel(int quad);
+int producer_lanes();  // DYN_PRODUCERS (default 1)
 int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st);
 
 }  // namespace dyn

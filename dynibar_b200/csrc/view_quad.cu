@@ -543,7 +543,8 @@ __global__ void __launch_bounds__(576, 1) view_quad_kernel(const __grid_constant
   const int n_iter = (int)((n_rows + 255) / 256);
 
   if (warp == W_PROD) {
-    if ((tid & 31) == 0) producer_loop<true, kQRing, kQStage>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) < a.producers)
+      producer_loop<true, kQRing, kQStage>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0, tid & 31, a.producers);
   } else if (warp == W_ISSUE) {
     issuer_loop<true, 2, kQRing, kQStage>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kQATile,
                                           a.dbg ? a.dbg + 256 : nullptr);

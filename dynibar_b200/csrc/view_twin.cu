@@ -41,11 +41,12 @@ using namespace fe;
 namespace {
 
 constexpr bool kTwinPP = true;  // ping-pong (measured 8% faster than lock-step, profiles/r01_kernels.md)
-constexpr int kTwinATile = 65536;  // K <= 256 in the per-view nets: 32 k-groups
-constexpr int T_B2 = 0, T_B4 = 48, T_B5 = 176, T_B6 = 304, T_W6V = 432, T_B7 = 560, T_W8 = 688,
-              T_MISC = 816, T_DFEAT = 832, T_CAMS = 880 /* 16 views x (P 12 + centre 3 + pad) */,
-              T_XCH = T_CAMS + 256;  // + 2 x [2][256] exchange
-constexpr int kTwinConst = T_XCH + 1024;
+constexpr int kTwinATile = 69632;  // K <= 256 (+ one k-step of bias columns): 34 k-groups
+// T_B5 / T_B7 hold log2(e) * bias, T_W6V / T_W8 hold ln(2) * weight (the hidden activations of vis_fc.0 and
+// vis_fc2.0 live on the exp2 scale); the biases of base_fc.2 and vis_fc.2 ride in the MMA
+constexpr int T_B2 = 0, T_B5 = 48, T_W6V = 176, T_B7 = 304, T_W8 = 432, T_MISC = 560, T_DFEAT = 576,
+              T_CAMS = 624 /* 16 views x (P 12 + centre 3 + pad) */, T_XCH = T_CAMS + 256;  // + 2 x [2][128] exchange
+constexpr int kTwinConst = T_XCH + 512;
 // NT = 128-row tiles per CTA: 2 -> one 576-thread CTA per SM (ping-pong between its tiles);
 // 1 -> two independent 320-thread CTAs per SM, each with one tile and a 2-slot weight ring, so
 // the tensor pipe is shared by two unsynchronised instruction streams.
@@ -127,12 +128,10 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       cst[T_CAMS + i] = j < 12 ? a.cams.P[vv][j] : (j < 15 ? a.cams.center[vv][j - 12] : 0.f);
     }
     for (int i = tid; i < 128; i += blockDim.x) {
-      cst[T_B4 + i] = prm[a.o_b4 + i];
-      cst[T_B5 + i] = prm[a.o_b5 + i];
-      cst[T_B6 + i] = prm[a.o_b6 + i];
-      cst[T_W6V + i] = prm[a.o_w6 + 128 * 128 + i];
-      cst[T_B7 + i] = prm[a.o_b7 + i];
-      cst[T_W8 + i] = prm[a.o_w8 + i];
+      cst[T_B5 + i] = prm[a.o_b5 + i] * 1.4426950408889634f;
+      cst[T_W6V + i] = prm[a.o_w6 + 128 * 128 + i] * 0.6931471805599453f;
+      cst[T_B7 + i] = prm[a.o_b7 + i] * 1.4426950408889634f;
+      cst[T_W8 + i] = prm[a.o_w8 + i] * 0.6931471805599453f;
     }
     if (tid < 48) cst[T_B2 + tid] = (ST && tid < kF) ? prm[a.o_b2 + tid] : 0.f;
     if (tid < 40) cst[T_DFEAT + tid] = (!ST && tid < kF) ? a.dfeat[tid] : 0.f;
@@ -152,7 +151,8 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
   const int n_iter = (int)((n_rows + ROWS - 1) / ROWS);
 
   if (warp == W_PROD) {
-    if ((tid & 31) == 0) producer_loop<PP, RING, kTwinStage>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0);
+    if ((tid & 31) < a.producers)
+      producer_loop<PP, RING, kTwinStage>(s_tab, a.nchunks, a.wimg, n_iter, ring, bar0, tid & 31, a.producers);
   } else if (warp == W_ISSUE) {
     issuer_loop<PP, NT, RING, kTwinStage>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kTwinATile,
                            a.dbg ? a.dbg + 128 : nullptr);
@@ -166,8 +166,15 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
     const int gl = t & (VP - 1);
     const int pair = warp & (4 * NT - 1);
     const int bt = PP ? tile : 0;  // barrier tile
-    float* xch5 = cst + T_XCH;        // [2][256] partial visibility logits of vis_fc
-    float* xch7 = cst + T_XCH + 512;  // [2][256] partial logits of vis_fc2
+    float* xch5 = cst + T_XCH;        // [2][128] partial visibility logits of vis_fc
+    float* xch7 = cst + T_XCH + 256;  // [2][128] partial logits of vis_fc2
+    static_assert(NT == 1, "exchange arrays are sized for one tile per CTA");
+    if (tw == 0) {
+      // persistent bias columns of base_fc.2 (K = 256 + 16): k-groups 32, 33 = [1, 1, 0 ...] (hi, lo)
+      float o[8] = {1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store8(arow, 256, o);
+      store8(arow, 264, z);
+    }
     uint32_t acc_cnt = 0;
     const float wh = a.w_img, hh = a.h_img;
     int dbg_n = 0;
@@ -457,7 +464,8 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
 
       const int c0 = 64 * tw;  // this twin's columns of the 128-wide layers
       TS();  // 8: F3 epilogue done
-      // ---- F4: x = ELU(base_fc.2) -> TMEM [128,256); A = x * w1 ----
+      // ---- F4: x = ELU(base_fc.2) -> TMEM [128,256); A = x (the pooling weight w1 of vis_fc.0's input is applied
+      //      to the accumulator in the next epilogue: W (w1 x) = w1 (W x)); bias folded, accumulator on the exp2 scale ----
       mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
       TS();  // 9: F4 acc ready
       tc_fence_after_sync();
@@ -467,12 +475,16 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         tmem_ld32(tacc + cb, acc);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = elu_fast(acc[i] + cst[T_B4 + cb + i]);
+        for (int i = 0; i < 32; ++i) acc[i] = elu_from_log2(acc[i]);
         tmem_st32(tacc + 128 + cb, acc);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] *= w1;
-#pragma unroll
         for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
+      }
+      if (tw == 1) {
+        // bias columns of vis_fc.2 (K = 128 + 16): k-groups 16, 17 (free once this layer's MMA has read them)
+        float o[8] = {1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store8(arow, 128, o);
+        store8(arow, 136, z);
       }
       tmem_wait_st();
       fence_proxy_async_smem();
@@ -493,13 +505,13 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            acc[i] = elu_fast(acc[i] + cst[T_B5 + cb + i]);
+            acc[i] = elu_log2(fmaf(acc[i], w1, cst[T_B5 + cb + i]));  // log2(e) * ELU(w1 (W x) + b)
             part = fmaf(acc[i], cst[T_W6V + cb + i], part);
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
         }
-        xch5[tw * 256 + t] = part;
+        xch5[tw * 128 + t] = part;
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
@@ -511,7 +523,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       TS();  // 13: F6 acc ready
       tc_fence_after_sync();
       // both twins arrived on a_ready before this MMA ran: the partial logits are visible
-      const float vlogit = cst[T_MISC + 0] + xch5[t] + xch5[256 + t];
+      const float vlogit = cst[T_MISC + 0] + xch5[t] + xch5[128 + t];
       const float vis1 = sigmoid_fast(elu_fast(vlogit)) * mask;
 #pragma unroll 1
       for (int cb = c0; cb < c0 + 64; cb += 32) {
@@ -520,22 +532,22 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         tmem_ld32(tacc + 128 + cb, xs);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) xs[i] += elu_fast(acc[i] + cst[T_B6 + cb + i]);
+        for (int i = 0; i < 32; ++i) xs[i] += elu_from_log2(acc[i]);
         tmem_st32(tacc + 128 + cb, xs);
+        // bf16(x) is both vis_fc2.0's operand (vis1 is applied to its accumulator) and, for the static net,
+        // the spill for the blending head (a bf16 tile image in view-slot row order, fused_engine.cuh)
+        uint4 pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          pk[i] = make_uint4(pack_bf16x2(xs[8 * i], xs[8 * i + 1]), pack_bf16x2(xs[8 * i + 2], xs[8 * i + 3]),
+                             pack_bf16x2(xs[8 * i + 4], xs[8 * i + 5]), pack_bf16x2(xs[8 * i + 6], xs[8 * i + 7]));
         if (ST && !(a.ablate & 2)) {
-          // spilled as a bf16 tile image (fused_engine.cuh) in view-slot row order: the blending
-          // head lands it in its operand tile with one bulk copy per 128 rows
           uint8_t* xo = reinterpret_cast<uint8_t*>(a.X) + tile_image_off((long long)it * ROWS + t, cb >> 3, 16);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(xo + i * 2048) =
-                make_uint4(pack_bf16x2(xs[8 * i], xs[8 * i + 1]), pack_bf16x2(xs[8 * i + 2], xs[8 * i + 3]),
-                           pack_bf16x2(xs[8 * i + 4], xs[8 * i + 5]), pack_bf16x2(xs[8 * i + 6], xs[8 * i + 7]));
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(xo + i * 2048) = pk[i];
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) xs[i] *= vis1;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, xs + 8 * g);
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(arow + ((cb >> 3) + i) * 2048) = pk[i];
       }
       tmem_wait_st();
       fence_proxy_async_smem();
@@ -557,13 +569,13 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            part = fmaf(elu_fast(acc[i] + cst[T_B7 + cb + i]), cst[T_W8 + cb + i], part);
+            part = fmaf(elu_log2(fmaf(acc[i], vis1, cst[T_B7 + cb + i])), cst[T_W8 + cb + i], part);
         }
-        xch7[tw * 256 + t] = part;
+        xch7[tw * 128 + t] = part;
       }
       TS();  // 16: F7 partial done
       pair_sync(pair);
-      const float v2 = cst[T_MISC + 1] + xch7[t] + xch7[256 + t];
+      const float v2 = cst[T_MISC + 1] + xch7[t] + xch7[128 + t];
       const float vis2 = sigmoid_fast(v2) * mask;
       if (ST && valid && tw == 0 && !(a.ablate & 2)) a.vis2[m] = vis2;
       const float vsum = group_sum<VP>(vis2);
@@ -659,12 +671,18 @@ int view_twin_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes,
   constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
   // fold_bias: the layer's bias rides in the map's kBiasHi / kBiasLo columns
   auto add = [&](const LinearP& l, int N, int Npad, int Kpad, std::vector<int> map, float scale = 1.f,
-                 bool fold_bias = false) {
+                 bool fold_bias = false, float bias_scale = -1.f) {
     HostLayer L;
     L.W = P + l.w; L.N = N; L.Kw = l.in; L.Npad = Npad; L.Kpad = Kpad; L.colmap = std::move(map);
-    L.scale = scale;
+    L.scale = scale; L.bias_scale = bias_scale;
     if (fold_bias) L.bias = P + l.b;
     append_layer(L, img, tab, 0, 0, 9, true, kTwinStage);
+  };
+  // identity columns 0..K-1 followed by one k-step whose first two columns carry the folded bias (hi, lo)
+  auto bias_map = [](int K) {
+    std::vector<int> m = identity_map(K, K + 16);
+    m[K] = kBiasHi; m[K + 1] = kBiasLo;
+    return m;
   };
   if (n->kind == DYN_NET_STATIC) {
     const StaticLayout& L = n->sl;
@@ -698,10 +716,10 @@ int view_twin_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes,
       }
     m3[103] = kBiasHi; m3[111] = kBiasLo;  // twin 0, slot 39 (unused): mean / var columns of group 4
     add(L.base0, 256, 256, 240, m3, kLog2e, true);
-    add(L.base2, 128, 128, 256, identity_map(256, 256), kLn2);
-    add(L.vis0, 128, 128, 128, identity_map(128, 128));
-    add(L.vis2, 128, 128, 128, identity_map(128, 128));
-    add(L.vis2_0, 128, 128, 128, identity_map(128, 128));
+    add(L.base2, 128, 128, 272, bias_map(256), 1.f, true, kLog2e);  // in: log2(e) ELU (x ln2), out: exp2 scale (x log2e)
+    add(L.vis0, 128, 128, 128, identity_map(128, 128), kLog2e);     // in: x (true units); w1 and bias in the epilogue
+    add(L.vis2, 128, 128, 144, bias_map(128), 1.f, true, kLog2e);   // rows 0..127 of vis_fc.2; in: log2(e) ELU
+    add(L.vis2_0, 128, 128, 128, identity_map(128, 128), kLog2e);   // vis1 and bias in the epilogue
   } else {
     const DynamicLayout& L = n->dl;
     // twin 0: channels 0..18 (3 groups, cols 0..71), twin 1: channels 19..34 (2 groups, cols 72..119)
@@ -714,10 +732,10 @@ int view_twin_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes,
     }
     m3[55] = kBiasHi; m3[63] = kBiasLo;  // twin 0, slot 23 (unused): mean / var columns of group 2
     add(L.base0, 256, 256, 128, m3, kLog2e, true);
-    add(L.base2, 128, 128, 256, identity_map(256, 256), kLn2);
-    add(L.vis0, 128, 128, 128, identity_map(128, 128));
-    add(L.vis2, 128, 128, 128, identity_map(128, 128));
-    add(L.vis2_0, 128, 128, 128, identity_map(128, 128));
+    add(L.base2, 128, 128, 272, bias_map(256), 1.f, true, kLog2e);  // in: log2(e) ELU (x ln2), out: exp2 scale (x log2e)
+    add(L.vis0, 128, 128, 128, identity_map(128, 128), kLog2e);     // in: x (true units); w1 and bias in the epilogue
+    add(L.vis2, 128, 128, 144, bias_map(128), 1.f, true, kLog2e);   // rows 0..127 of vis_fc.2; in: log2(e) ELU
+    add(L.vis2_0, 128, 128, 128, identity_map(128, 128), kLog2e);   // vis1 and bias in the epilogue
   }
   const size_t img_bytes = (img.size() + 255) & ~(size_t)255;
   const size_t need = img_bytes + tab.size() * sizeof(FusedChunk);

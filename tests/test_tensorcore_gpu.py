@@ -94,10 +94,66 @@ def test_bf16_mode_end_to_end(golden, name):
   finally:
     rr.set_precision("fp32")
   g, w = got[key], want[key]
-  assert_close_frac("rgb", g["rgb"], w["rgb"], rtol=0, atol=2e-3, max_bad_frac=0.02)
-  assert_close_frac("weights", g["weights"], w["weights"], rtol=0, atol=2e-3, max_bad_frac=0.02)
-  assert_close_frac("depth", g["depth"], w["depth"], rtol=2e-3, atol=1e-3, max_bad_frac=0.02)
+  # only the stress rigs put samples on in-bounds discontinuities (util.assert_close_frac)
+  bad = 0.02 if cfg.get("stress") else 1e-3
+  assert_close_frac("rgb", g["rgb"], w["rgb"], rtol=0, atol=2e-3, max_bad_frac=bad)
+  assert_close_frac("weights", g["weights"], w["weights"], rtol=0, atol=2e-3, max_bad_frac=bad)
+  assert_close_frac("depth", g["depth"], w["depth"], rtol=2e-3, atol=1e-3, max_bad_frac=bad)
   assert orc.psnr(g["rgb"].cpu(), w["rgb"]) > 50.0
+
+
+# The benchmarked mode at the benchmark's own shapes, against the ORACLE (not the library's fp32 path):
+# BASELINE configs[1] (512x288, 64+64 samples, 8+8 views), the view counts eval_nvidia.py really uses
+# (7 dynamic + 11 static, eval_nvidia.py:92-119) and the config-4 mono rig (10 dynamic incl. 3 virtual +
+# 15 static views).  No stress rig -> no discontinuity allowance beyond 1e-3 of the elements.
+BENCH_SHAPES = {
+    "bench_8+8": dict(mono=False, H=288, W=512, V_dy=8, V_st=8, rays=96, N_samples=64, N_importance=64, num_vv=0,
+                      inv_uniform=True, anti_alias_pooling=1, mask_rgb=0, seed=0, stress=False),
+    "nvidia_7+11": dict(mono=False, H=288, W=512, V_dy=7, V_st=11, rays=64, N_samples=64, N_importance=64,
+                        num_vv=0, inv_uniform=True, anti_alias_pooling=1, mask_rgb=0, seed=3, stress=False),
+    "mono_10+15": dict(mono=True, H=270, W=480, V_dy=10, V_st=15, rays=96, N_samples=64, N_importance=0,
+                       num_vv=3, inv_uniform=True, anti_alias_pooling=1, mask_rgb=1, seed=4, stress=False),
+}
+
+
+@pytest.mark.parametrize("name", list(BENCH_SHAPES))
+def test_bf16_mode_against_oracle_at_benchmark_shapes(name):
+  from dynibar_b200 import render_ray as rr
+  from dynibar_b200.projection import Projector
+  cfg = BENCH_SHAPES[name]
+  batch, feat_c, feat_f, frame, t, offs, model, args = scenes.build(cfg)
+  d = lambda x: synthetic.to_device(x, DEV)
+  with torch.no_grad():
+    if cfg["mono"]:
+      want = orc.render_rays_mono(frame, t, offs, batch, model, feat_c, None, cfg["N_samples"], args,
+                                  inv_uniform=True, det=True, is_train=False, num_vv=cfg["num_vv"])
+      keys = ("outputs_coarse_ref", "outputs_coarse_ref_dy", "outputs_coarse_st")
+    else:
+      want = orc.render_rays_mv(frame, t, offs, batch, model, None, feat_c, feat_f, cfg["N_samples"], args,
+                                inv_uniform=True, N_importance=cfg["N_importance"], det=True, is_train=False)
+      keys = ("outputs_fine_ref", "outputs_fine_ref_dy")
+  m = synthetic.model_to(model, DEV)
+  rr.set_precision("bf16")
+  try:
+    if cfg["mono"]:
+      got = rr.render_rays_mono(frame, t, offs, d(batch), m, d(feat_c), Projector(DEV), cfg["N_samples"], args,
+                                inv_uniform=True, det=True, is_train=False, num_vv=cfg["num_vv"])
+    else:
+      got = rr.render_rays_mv(frame, t, offs, d(batch), m, Projector(DEV), d(feat_c), d(feat_f),
+                              cfg["N_samples"], args, inv_uniform=True, N_importance=cfg["N_importance"],
+                              det=True, is_train=False)
+  finally:
+    rr.set_precision("fp32")
+  for key in keys:
+    g, w = got[key], want[key]
+    for kk in ("rgb", "weights", "depth"):
+      err = (g[kk].cpu() - w[kk]).abs().max().item()
+      print("%s %s/%s max abs err %.3e" % (name, key, kk, err))
+    assert_close_frac(key + "/rgb", g["rgb"], w["rgb"], rtol=0, atol=2e-3, max_bad_frac=1e-3)
+    assert_close_frac(key + "/weights", g["weights"], w["weights"], rtol=0, atol=2e-3, max_bad_frac=1e-3)
+    assert_close_frac(key + "/depth", g["depth"], w["depth"], rtol=2e-3, atol=1e-3, max_bad_frac=1e-3)
+    assert torch.equal(g["mask"].cpu(), w["mask"])
+    assert orc.psnr(g["rgb"].cpu(), w["rgb"]) > 50.0
 
 
 @pytest.mark.parametrize("name", ["mv_small", "mv_linear", "mono_small"])
@@ -245,8 +301,8 @@ def test_config4_sample_counts_use_simt_attention_for_192_samples():
   ref = _run_mode(cfg, "fp32")["outputs_fine_ref"]
   got = _run_mode(cfg, "bf16")["outputs_fine_ref"]
   assert got["weights"].shape[-1] == 192
-  assert_close_frac("rgb", got["rgb"], ref["rgb"], rtol=0, atol=2e-3, max_bad_frac=0.03)
-  assert_close_frac("weights", got["weights"], ref["weights"], rtol=0, atol=2e-3, max_bad_frac=0.03)
+  assert_close_frac("rgb", got["rgb"], ref["rgb"], rtol=0, atol=2e-3, max_bad_frac=1e-3)
+  assert_close_frac("weights", got["weights"], ref["weights"], rtol=0, atol=2e-3, max_bad_frac=1e-3)
 
 
 def test_more_than_16_views_falls_back_to_staged_tensor_core_layers():
@@ -254,7 +310,7 @@ def test_more_than_16_views_falls_back_to_staged_tensor_core_layers():
              inv_uniform=True, anti_alias_pooling=1, mask_rgb=0, seed=32, stress=False)
   ref = _run_mode(cfg, "fp32")["outputs_fine_ref"]
   got = _run_mode(cfg, "bf16")["outputs_fine_ref"]
-  assert_close_frac("rgb", got["rgb"], ref["rgb"], rtol=0, atol=2e-3, max_bad_frac=0.03)
+  assert_close_frac("rgb", got["rgb"], ref["rgb"], rtol=0, atol=2e-3, max_bad_frac=1e-3)
 
 
 @pytest.mark.parametrize("rays", [0, 1, 255, 257])
@@ -321,5 +377,5 @@ def test_bf16_full_size_properties():
   for k in ("ray_o", "ray_d", "uv_grid"):
     sub[k] = b[k][:512].contiguous()
   ref = run(sub, "fp32")
-  assert_close_frac("rgb", full["rgb"][:512], ref["rgb"], rtol=0, atol=2e-3, max_bad_frac=0.02)
+  assert_close_frac("rgb", full["rgb"][:512], ref["rgb"], rtol=0, atol=2e-3, max_bad_frac=1e-3)
   assert orc.psnr(full["rgb"][:512].cpu(), ref["rgb"].cpu()) > 50.0
