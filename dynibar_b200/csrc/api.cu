@@ -106,8 +106,8 @@ size_t dyn_net_param_count(int kind) {
 
 size_t dyn_net_packed_bytes(int kind) {
   switch (kind) {
-    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes + view_twin_bytes(kind) + view_quad_bytes(kind) + fused_chain_bytes(kind);
-    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes + view_twin_bytes(kind) + view_quad_bytes(kind) + fused_chain_bytes(kind);
+    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes + view_twin_bytes(kind) + view_quad_bytes(kind) + fused_chain_bytes(kind) + twin_chain_bytes(kind);
+    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes + view_twin_bytes(kind) + view_quad_bytes(kind) + fused_chain_bytes(kind) + twin_chain_bytes(kind);
     case DYN_NET_MOTION: return (size_t)motion_layout(8).all.packed_bytes + fused_chain_bytes(kind);
     default: return 0;
   }
@@ -177,6 +177,8 @@ int dyn_net_create(int kind, const float* params, size_t n_params, void* packed,
         cur += view_quad_bytes(kind);
       }
       if (!rc) rc = fused_chain_build(n, hp, cur, fused_chain_bytes(kind), (cudaStream_t)stream);
+      cur += fused_chain_bytes(kind);
+      if (!rc) rc = twin_chain_build(n, hp, cur, twin_chain_bytes(kind), (cudaStream_t)stream);
       free(hp);
       if (rc) { free(n); return rc; }
     }

@@ -122,6 +122,9 @@ struct dyn_net {
   // row-local fused chains (chains_fused.cu): motion: [0]; aggregation nets:
   // [0] point stage 1, [1] point stage 2, [2] static blending head
   dyn::ChainImage chain[3];
+  // the same chains in the twin-warp structure (chains_twin.cu): [0] point stage 1, [1] point stage 2,
+  // [2] static blending head
+  dyn::ChainImage chain_tw[3];
   // twin-warp per-view stage (view_twin.cu): weight images in its column layout
   dyn::ChainImage twin;
   // quad-schedule per-view stage (view_quad.cu)

@@ -296,6 +296,8 @@ struct HostLayer {
   float scale = 1.f;
   float bias_scale = -1.f;  // < 0: same as `scale` (differs when the layer CONSUMES a log2-scaled operand
                             // and PRODUCES an exp2-scale accumulator: weights x ln2 x log2e = 1, bias x log2e)
+  std::vector<float> colscale;  // optional, size Kpad: extra factor per OPERAND column (operand tiles that mix
+                                // exp2-scale activations with true-scale encodings)
 };
 constexpr int kBiasHi = -2, kBiasLo = -3;
 inline float bf2f(uint16_t h) {
@@ -329,7 +331,7 @@ inline void append_layer(const HostLayer& L, std::vector<uint8_t>& img, std::vec
         float val = 0.f;
         if (n < L.N) {
           if (col >= 0) {
-            val = L.W[(size_t)n * L.Kw + col] * L.scale;
+            val = L.W[(size_t)n * L.Kw + col] * L.scale * (L.colscale.empty() ? 1.f : L.colscale[k0 * 16 + kk]);
           } else if (L.bias != nullptr && (col == kBiasHi || col == kBiasLo)) {
             const float b = L.bias[n] * (L.bias_scale >= 0.f ? L.bias_scale : L.scale), hi = bf2f(f2bf(b));
             val = col == kBiasHi ? hi : b - hi;

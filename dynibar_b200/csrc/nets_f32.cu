@@ -910,7 +910,8 @@ static int run_point_fused(const dyn_net* n, const float* G, long long P, int R,
     DYN_LAUNCH_CHECK();
     p1.posenc = posenc_tab;
   }
-  RUN(launch_point1_fused(n, p1, st));
+  if (use_twin_chains()) RUN(launch_point1_twin(n, p1, st));
+  else RUN(launch_point1_fused(n, p1, st));
   if (attention_tc_supported(S)) {
     RUN(launch_attention_tc(Qb, Kb, Vb, t.nvalid, P, S, Ob, st));
   } else {
@@ -925,6 +926,7 @@ static int run_point_fused(const dyn_net* n, const float* G, long long P, int R,
     DYN_LAUNCH_CHECK();
   }
   p2.O = Ob; p2.g2 = t.G2; p2.nvalid = t.nvalid; p2.P = P; p2.S = S;
+  if (use_twin_chains()) return launch_point2_twin(n, p2, st);
   return launch_point2_fused(n, p2, st);
 }
 
@@ -939,6 +941,7 @@ __global__ void rows_to_image_kernel(const float* __restrict__ src, int ld, int 
   float v[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = (8 * kg + i < ncols) ? src[row * ld + 8 * kg + i] : 0.f;
+  if (KG == 34 && kg == 33) { v[0] = 1.f; v[1] = 1.f; }  // bias columns of the geometry_fc layers (chains_twin.cu)
   *reinterpret_cast<uint4*>(img + fe::tile_image_off(row, kg, KG)) =
       make_uint4(fe::pack_bf16x2(v[0], v[1]), fe::pack_bf16x2(v[2], v[3]), fe::pack_bf16x2(v[4], v[5]),
                  fe::pack_bf16x2(v[6], v[7]));
@@ -1036,7 +1039,8 @@ int net_static_fused(const dyn_net* n, const float* pts, const float* ray_o, con
       memset(&rh, 0, sizeof(rh));
       rh.X = d.X; rh.vis2 = d.vis2; rh.ray_diff = d.rd; rh.mask_eff = d.meff; rh.rgb_in = d.rgbin;
       rh.GW = d.ch; rh.sigma = d.sig; rh.P = P; rh.V = V; rh.raw = raw + p0 * 4;
-      RUN(launch_rgbhead_fused(n, rh, st));
+      if (use_twin_chains()) RUN(launch_rgbhead_twin(n, rh, st));
+      else RUN(launch_rgbhead_fused(n, rh, st));
     }
     (void)prec; (void)M;
   }

@@ -25,6 +25,15 @@ static bool use_twin_kernel() {
   return g_view_kernel == 0;
 }
 
+bool use_twin_chains() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DYN_CHAINS");
+    v = (e != nullptr && e[0] == 'f') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int producer_lanes() {
   static int v = -1;
   if (v < 0) {

@@ -130,6 +130,14 @@ int launch_point1_fused(const dyn_net* n, Point1Args& a, cudaStream_t st);
 int launch_point2_fused(const dyn_net* n, Point2Args& a, cudaStream_t st);
 int launch_rgbhead_fused(const dyn_net* n, RgbHeadArgs& a, cudaStream_t st);
 
+// twin-warp versions of the row-local chains (chains_twin.cu); DYN_CHAINS=fused selects the round-1 kernels
+size_t twin_chain_bytes(int kind);
+int twin_chain_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes, cudaStream_t st);
+int launch_point1_twin(const dyn_net* n, Point1Args& a, cudaStream_t st);
+int launch_point2_twin(const dyn_net* n, Point2Args& a, cudaStream_t st);
+int launch_rgbhead_twin(const dyn_net* n, RgbHeadArgs& a, cudaStream_t st);
+bool use_twin_chains();
+
 // twin-warp per-view stage (view_twin.cu)
 size_t view_twin_bytes(int kind);
 int view_twin_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes, cudaStream_t st);

@@ -494,7 +494,7 @@ struct QuadOps {
       if (gl == 0 && q == 0) {
         *reinterpret_cast<uint4*>(gi + tile_image_off(c.pl, 32, 34)) =
             make_uint4(pack_bf16x2(W / (float)a.V, 0.f), 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(gi + tile_image_off(c.pl, 33, 34)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(gi + tile_image_off(c.pl, 33, 34)) = make_uint4(0x3F803F80u, 0u, 0u, 0u);  // 1, 1: bias columns of geometry_fc
         a.nvalid[c.pl] = nval;
       }
     }

@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           if (gl == 0 && tw == 0) {
             *reinterpret_cast<uint4*>(gi + tile_image_off(pl, 32, 34)) =
                 make_uint4(pack_bf16x2(W / (float)a.V, 0.f), 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(gi + tile_image_off(pl, 33, 34)) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(gi + tile_image_off(pl, 33, 34)) = make_uint4(0x3F803F80u, 0u, 0u, 0u);  // 1, 1: bias columns of geometry_fc
             a.nvalid[pl] = nval;
           }
         }
