@@ -234,6 +234,17 @@ int dyn_flow_sceneflow(const float* weights, const float* pts_seq,
                        int frame_idx, int sf_k, int n_flow, int R, int S,
                        float* flows, float* exp_sf, void* stream);
 
+/* ---- f1: 2-D feature encoder, ResNet.forward as the reference runs it (feature_network.py:302-311) ----
+ * conv 7x7 stride 2 (reflect) -> InstanceNorm -> ReLU -> layer1 (3 BasicBlocks, the first with stride 2)
+ * -> 1x1 conv -> coarse (channels 0..31) | fine (channels 32..63).  images [N,3,H,W] fp32;
+ * coarse, fine [N,32,H/4,W/4].  `params` = the executed parameters in state_dict order
+ * (dynibar_b200/feature_network.py: _EXECUTED), dyn_encoder_param_count() floats. */
+size_t dyn_encoder_param_count(void);
+size_t dyn_encoder_workspace_bytes(int N, int H, int W);
+int dyn_encoder_forward(const float* params, size_t n_params, const float* images,
+                        int N, int H, int W, float* coarse, float* fine,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- unit-test hook: the fused per-point stage (geometry_fc -> ray transformer
  * -> heads; mlp_network.py:283-315 / :496-506) on caller-provided pooled
  * features G [R*S, 272] (257 used) and nvalid [R*S].  Outputs g2 [R*S,128] (plain
