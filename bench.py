@@ -54,8 +54,8 @@ def parse():
   ap.add_argument("--cpu-rays", type=int, default=512, help="rays per timed chunk of the in-line cpu_baseline")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-extras", action="store_true", help="skip the kernel-timing pass, the 7+11-view line and weak_scaling")
-  ap.add_argument("--view-kernel", default="twin", choices=["twin", "quad"],
-                  help="per-view stage kernel: twin-warp (default) or the quad schedule (comparison)")
+  ap.add_argument("--view-kernel", default="default", choices=["default", "twin", "quad", "pipe"],
+                  help="per-view stage kernel: library default, twin-warp, quad schedule, or sub-round pipelined twin")
   return ap.parse_args()
 
 
@@ -216,7 +216,7 @@ def main():
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
   rr.set_precision(a.precision)
-  _lib.lib.dyn_debug_set_view_kernel(1 if a.view_kernel == "quad" else 0)
+  _lib.lib.dyn_debug_set_view_kernel({"default": -1, "twin": 0, "quad": 1, "pipe": 2}[a.view_kernel])
   pin = lambda x: x.pin_memory() if torch.is_tensor(x) else x
   P = Projector(dev)
   SRC_KEYS = ("src_rgbs", "static_src_rgbs")

@@ -106,8 +106,8 @@ size_t dyn_net_param_count(int kind) {
 
 size_t dyn_net_packed_bytes(int kind) {
   switch (kind) {
-    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes + view_twin_bytes(kind) + view_quad_bytes(kind) + fused_chain_bytes(kind) + twin_chain_bytes(kind);
-    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes + view_twin_bytes(kind) + view_quad_bytes(kind) + fused_chain_bytes(kind) + twin_chain_bytes(kind);
+    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes + view_twin_bytes(kind) + view_quad_bytes(kind) + view_twin3_bytes(kind) + fused_chain_bytes(kind) + twin_chain_bytes(kind);
+    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes + view_twin_bytes(kind) + view_quad_bytes(kind) + view_twin3_bytes(kind) + fused_chain_bytes(kind) + twin_chain_bytes(kind);
     case DYN_NET_MOTION: return (size_t)motion_layout(8).all.packed_bytes + fused_chain_bytes(kind);
     default: return 0;
   }
@@ -175,6 +175,8 @@ int dyn_net_create(int kind, const float* params, size_t n_params, void* packed,
         cur += view_twin_bytes(kind);
         if (!rc) rc = view_quad_build(n, hp, cur, view_quad_bytes(kind), (cudaStream_t)stream);
         cur += view_quad_bytes(kind);
+        if (!rc) rc = view_twin3_build(n, hp, cur, view_twin3_bytes(kind), (cudaStream_t)stream);
+        cur += view_twin3_bytes(kind);
       }
       if (!rc) rc = fused_chain_build(n, hp, cur, fused_chain_bytes(kind), (cudaStream_t)stream);
       cur += fused_chain_bytes(kind);
@@ -213,7 +215,7 @@ int dyn_rgbs_rgba(const float* src_rgbs, float* out_rgba, int V, int H, int W, v
   return launch_rgb_to_rgba(src_rgbs, out_rgba, (long long)V * H * W, (cudaStream_t)stream);
 }
 
-void dyn_debug_set_view_kernel(int quad) { set_view_kernel(quad); }
+void dyn_debug_set_view_kernel(int which) { set_view_kernel(which); }
 
 static long long* g_view_dbg = nullptr;
 void dyn_debug_set_view_timestamps(long long* dev_buf) { g_view_dbg = dev_buf; }

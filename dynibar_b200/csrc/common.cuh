@@ -129,6 +129,8 @@ struct dyn_net {
   dyn::ChainImage twin;
   // quad-schedule per-view stage (view_quad.cu)
   dyn::ChainImage quad;
+  // sub-round pipelined twin kernel (view_twin3.cu)
+  dyn::ChainImage twin3;
 };
 
 // ---- device helpers ---------------------------------------------------------

@@ -207,7 +207,8 @@ __device__ __forceinline__ void producer_loop(const FusedChunk* __restrict__ chu
 
 // Called by ALL 32 lanes of the issuer warp (converged).
 // FusedChunk.flags: 1 = wait for a_ready before this chunk, 2 = last chunk of a
-// round (commit acc_full), 8 = first k-step overwrites D (start of a layer);
+// round (commit acc_full), 4 = wait for the second operand barrier (one-tile kernels: the
+// a_ready slot of tile 1) before this chunk, 8 = first k-step overwrites D (start of a layer);
 // d_col = accumulator column offset inside the tile's 256-column TMEM region.
 // NT = 128-row tiles per CTA (1 or 2), RING = weight-ring slots in use.
 template <bool PP, int NT = 2, int RING = kRing, int STAGE = kStageBytes>
@@ -218,7 +219,7 @@ __device__ __forceinline__ void issuer_loop(const FusedChunk* __restrict__ chunk
   // Entered by the whole (converged) warp; ONE elected lane then runs the loop alone, so every
   // address / descriptor stays in uniform registers and no per-chunk warp re-convergence is needed.
   if (elect_one()) {
-    uint32_t cnt = 0, a_cnt[2] = {0, 0};
+    uint32_t cnt = 0, a_cnt[2] = {0, 0}, a2_cnt = 0;
     long long t_a = 0, t_w = 0, t_begin = clock64();
     const uint32_t a_addr[2] = {smem_u32(smem), smem_u32(smem + a_tile_bytes)};
     for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
@@ -231,6 +232,10 @@ __device__ __forceinline__ void issuer_loop(const FusedChunk* __restrict__ chunk
             if (ch.flags & 1) {
               mbar_wait(bar_aready(bar0, PP ? rep : 0, RING), a_cnt[PP ? rep : 0] & 1);
               ++a_cnt[PP ? rep : 0];
+            }
+            if (!PP && NT == 1 && (ch.flags & 4)) {  // second operand barrier of a two-sub-round layer
+              mbar_wait(bar_aready(bar0, 1, RING), a2_cnt & 1);
+              ++a2_cnt;
             }
             long long t1 = dbg ? clock64() : 0;
             const uint32_t st = cnt % RING;
@@ -340,6 +345,60 @@ inline void append_layer(const HostLayer& L, std::vector<uint8_t>& img, std::vec
         dst[tile_off((uint32_t)L.Npad, (uint32_t)n, (uint32_t)kk) / 2] = f2bf(val);
       }
     tab.push_back(ch);
+  }
+}
+
+// A layer issued in SUB-ROUNDS: `plan[r]` lists the runs (first k-step, number of k-steps) of operand columns
+// that sub-round r consumes; the issuer waits for one operand arrival round per sub-round (chunk flag 1) and
+// signals the epilogue only after the last one (flag 2).  The row warps arrive after every block of operand
+// columns they finish, so the k-steps over finished columns overlap the epilogue of the remaining ones.
+// Chunk c of a run starting at k-step k0 reads the operand tile at k-group a_kgroup0 + 2 * (k0 + ...).
+using LayerPlan = std::vector<std::vector<std::pair<int, int>>>;
+inline void append_layer_plan(const HostLayer& L, std::vector<uint8_t>& img, std::vector<FusedChunk>& tab,
+                              int d_col, int a_kgroup0, const LayerPlan& plan, int stage_bytes = kStageBytes) {
+  int steps_per_chunk = stage_bytes / (L.Npad * 32);
+  if (steps_per_chunk > 8) steps_per_chunk = 8;
+  bool first_chunk = true;
+  for (size_t r = 0; r < plan.size() && r < 2; ++r) {  // at most two sub-rounds (two operand barriers)
+    bool first_of_round = true;
+    for (size_t q = 0; q < plan[r].size(); ++q) {
+      const int run0 = plan[r][q].first, run1 = run0 + plan[r][q].second;
+      for (int k0 = run0; k0 < run1; k0 += steps_per_chunk) {
+        const int ks = (run1 - k0) < steps_per_chunk ? (run1 - k0) : steps_per_chunk;
+        const bool last = r + 1 == plan.size() && q + 1 == plan[r].size() && k0 + ks >= run1;
+        FusedChunk ch;
+        ch.off = (uint32_t)img.size();
+        ch.bytes = (uint32_t)(L.Npad * 32 * ks);
+        ch.npad = (uint16_t)L.Npad;
+        ch.ksteps = (uint8_t)ks;
+        // sub-round 0 waits on the operand barrier (flag 1), sub-round 1 on the SECOND operand barrier (flag 4):
+        // a row thread arrives on each of them exactly once per layer -- with a single barrier a fast thread's
+        // second arrival could complete the phase that a slow thread has not reached yet
+        ch.flags = (uint8_t)((first_of_round ? (r == 0 ? 1 : 4) : 0) | (first_chunk ? 8 : 0) | (last ? 2 : 0));
+        ch.a_kgroup = (uint16_t)(a_kgroup0 + k0 * 2);
+        ch.d_col = (uint16_t)d_col;
+        img.resize(img.size() + ch.bytes, 0);
+        uint16_t* dst = reinterpret_cast<uint16_t*>(img.data() + ch.off);
+        const float bs = L.bias_scale >= 0.f ? L.bias_scale : L.scale;
+        for (int n = 0; n < L.Npad; ++n)
+          for (int kk = 0; kk < ks * 16; ++kk) {
+            const int col = L.colmap[k0 * 16 + kk];
+            float val = 0.f;
+            if (n < L.N) {
+              if (col >= 0) {
+                val = L.W[(size_t)n * L.Kw + col] * L.scale * (L.colscale.empty() ? 1.f : L.colscale[k0 * 16 + kk]);
+              } else if (L.bias != nullptr && (col == kBiasHi || col == kBiasLo)) {
+                const float b = L.bias[n] * bs, hi = bf2f(f2bf(b));
+                val = col == kBiasHi ? hi : b - hi;
+              }
+            }
+            dst[tile_off((uint32_t)L.Npad, (uint32_t)n, (uint32_t)kk) / 2] = f2bf(val);
+          }
+        tab.push_back(ch);
+        first_of_round = false;
+        first_chunk = false;
+      }
+    }
   }
 }
 

@@ -12,17 +12,20 @@
 
 namespace dyn {
 
-// Two schedules of the same per-tile work: the twin-warp kernel (view_twin.cu: two independent CTAs per SM,
-// default -- it is the faster one, profiles/r02_view_kernels.md) and the quad kernel (view_quad.cu: one CTA
-// per SM alternating between two tiles; DYN_VIEW_KERNEL=quad or dyn_debug_set_view_kernel(1)).
-static int g_view_kernel = -1;  // 0 twin, 1 quad
-void set_view_kernel(int quad) { g_view_kernel = quad ? 1 : 0; }
-static bool use_twin_kernel() {
+constexpr int kDefaultViewKernel = 0;
+
+// Three schedules of the same per-tile work: 0 = the twin-warp kernel (view_twin.cu: two independent CTAs per
+// SM), 1 = the quad kernel (view_quad.cu: one CTA per SM alternating between two tiles), 2 = the twin-warp
+// kernel with sub-round pipelined layers (view_twin3.cu).  DYN_VIEW_KERNEL=twin|quad|pipe or
+// dyn_debug_set_view_kernel(); profiles/r02_view_kernels.md has the comparison.
+static int g_view_kernel = -1;
+void set_view_kernel(int which) { g_view_kernel = (which >= 0 && which <= 2) ? which : -1; }
+static int view_kernel() {
   if (g_view_kernel < 0) {
     const char* e = getenv("DYN_VIEW_KERNEL");
-    g_view_kernel = (e != nullptr && e[0] == 'q') ? 1 : 0;
+    g_view_kernel = e == nullptr ? kDefaultViewKernel : (e[0] == 'q' ? 1 : (e[0] == 'p' ? 2 : 0));
   }
-  return g_view_kernel == 0;
+  return g_view_kernel;
 }
 
 bool use_twin_chains() {
@@ -61,8 +64,11 @@ int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
     a.o_w8 = L.vis2_2.w; a.o_b8 = L.vis2_2.b; a.o_s = -1;
     a.anti_alias = 0; a.mask_rgb = 0;
   }
-  if (use_twin_kernel()) return launch_view_twin(n, a, V, st);
-  return launch_view_quad(n, a, V, st);
+  switch (view_kernel()) {
+    case 1: return launch_view_quad(n, a, V, st);
+    case 2: return launch_view_twin3(n, a, V, st);
+    default: return launch_view_twin(n, a, V, st);
+  }
 }
 
 }  // namespace dyn

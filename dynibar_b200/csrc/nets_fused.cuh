@@ -143,12 +143,17 @@ size_t view_twin_bytes(int kind);
 int view_twin_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes, cudaStream_t st);
 int launch_view_twin(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st);
 
+// sub-round pipelined twin-warp per-view stage (view_twin3.cu)
+size_t view_twin3_bytes(int kind);
+int view_twin3_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes, cudaStream_t st);
+int launch_view_twin3(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st);
+
 // quad-schedule per-view stage (view_quad.cu): one CTA per SM, two tiles, four threads per row
 size_t view_quad_bytes(int kind);
 int view_quad_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes, cudaStream_t st);
 int launch_view_quad(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st);
 
-void set_view_kernel(int quad);
+void set_view_kernel(int which);
 int producer_lanes();  // DYN_PRODUCERS (default 1)
 int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st);
 

@@ -274,11 +274,11 @@ int dyn_debug_pack_layer(const float* W, const float* bias, int N, int Kw, int N
  * 128-row tile: the layout activations use between the fused kernels. */
 size_t dyn_debug_tile_image_off(long long row, int kgroup, int kgroups);
 
-/* comparison hook: 0 (default) runs the fused per-view stage with the twin-warp kernel
- * (csrc/view_twin.cu: two independent CTAs per SM), 1 with the quad-schedule kernel
- * (csrc/view_quad.cu: one CTA per SM alternating between two tiles); the environment variable
- * DYN_VIEW_KERNEL=quad sets the initial value. */
-void dyn_debug_set_view_kernel(int quad);
+/* comparison hook: which kernel runs the fused per-view stage: 0 = twin-warp kernel (csrc/view_twin.cu: two
+ * independent CTAs per SM), 1 = quad-schedule kernel (csrc/view_quad.cu: one CTA per SM alternating between
+ * two tiles), 2 = twin-warp kernel with sub-round pipelined layers (csrc/view_twin3.cu).  The environment
+ * variable DYN_VIEW_KERNEL=twin|quad|pipe sets the initial value. */
+void dyn_debug_set_view_kernel(int which);
 
 /* profiling hook: when set, block 0 of the fused static per-view kernel writes clock64()
  * phase timestamps ([2 twins][64]) into dev_buf (profiles/scripts/prof_phases.py). */

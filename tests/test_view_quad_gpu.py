@@ -28,9 +28,9 @@ def _inputs(V_dy, V_st, rays, S, seed, stress=False, mask_rgb=0):
   return b, fc, m, pts, seq, float(t[0].float())
 
 
-def _run(b, fc, m, pts, seq, tt, twin):
+def _run(b, fc, m, pts, seq, tt, twin=False, kernel=None):
   from dynibar_b200 import render_ray as rr
-  _lib.lib.dyn_debug_set_view_kernel(0 if twin else 1)
+  _lib.lib.dyn_debug_set_view_kernel(kernel if kernel is not None else (0 if twin else 1))
   try:
     ray_dir = torch.nn.functional.normalize(b["ray_d"], dim=-1)
     raw_st, m_st = rr.net_static_fused(m.net_coarse_st, pts, b["ray_o"], b["ray_d"], b["camera"],
@@ -40,7 +40,7 @@ def _run(b, fc, m, pts, seq, tt, twin):
                                         b["src_cameras"], rr.featmaps_channels_last(fc[0]), tt)
     torch.cuda.synchronize()
   finally:
-    _lib.lib.dyn_debug_set_view_kernel(0)
+    _lib.lib.dyn_debug_set_view_kernel(-1)  # back to the library default
   return raw_st, m_st, raw_dy, m_dy
 
 
@@ -51,10 +51,11 @@ def _run(b, fc, m, pts, seq, tt, twin):
     (3, 2, 33, 16, True, 0),       # tiny: a single partially filled tile
     (16, 16, 40, 32, False, 0),    # full 16-slot groups
 ])
-def test_quad_kernel_matches_twin_kernel(V_dy, V_st, rays, S, stress, mask_rgb):
+@pytest.mark.parametrize("kernel", [1, 2])  # 1 = quad schedule, 2 = sub-round pipelined twin kernel
+def test_quad_kernel_matches_twin_kernel(V_dy, V_st, rays, S, stress, mask_rgb, kernel):
   inp = _inputs(V_dy, V_st, rays, S, seed=V_dy * 100 + V_st, stress=stress, mask_rgb=mask_rgb)
-  q = _run(*inp, twin=False)
-  t = _run(*inp, twin=True)
+  q = _run(*inp, kernel=kernel)
+  t = _run(*inp, kernel=0)
   assert torch.equal(q[1], t[1]) and torch.equal(q[3], t[3])  # projector masks: pure fp32 geometry
   for name, a, b, mask in (("st", q[0], t[0], q[1]), ("dy", q[2], t[2], q[3])):
     assert torch.isfinite(a[..., :3]).all()
@@ -64,19 +65,20 @@ def test_quad_kernel_matches_twin_kernel(V_dy, V_st, rays, S, stress, mask_rgb):
     assert_close_frac("sigma_" + name, a[..., 3][valid], b[..., 3][valid], rtol=0, atol=2e-2, max_bad_frac=1e-3)
 
 
-def test_quad_kernel_is_deterministic_and_chunk_invariant():
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+def test_quad_kernel_is_deterministic_and_chunk_invariant(kernel):
   """rows are independent: evaluating a prefix of the rays gives bit-identical results (different
   grid size, different tile pairing), and repeated launches are bit-identical."""
   from dynibar_b200 import render_ray as rr
   b, fc, m, pts, seq, tt = _inputs(8, 8, 520, 32, seed=5)
-  full = _run(b, fc, m, pts, seq, tt, twin=False)
-  again = _run(b, fc, m, pts, seq, tt, twin=False)
+  full = _run(b, fc, m, pts, seq, tt, kernel=kernel)
+  again = _run(b, fc, m, pts, seq, tt, kernel=kernel)
   for x, y in zip(full, again):
     assert torch.equal(x, y)
   n = 200
   bs = dict(b)
   for k in ("ray_o", "ray_d", "uv_grid"):
     bs[k] = b[k][:n].contiguous()
-  part = _run(bs, fc, m, pts[:n].contiguous(), seq[:, :n].contiguous(), tt, twin=False)
+  part = _run(bs, fc, m, pts[:n].contiguous(), seq[:, :n].contiguous(), tt, kernel=kernel)
   for x, y in zip(full, part):
     assert torch.equal(x[:n], y)
