@@ -71,6 +71,8 @@ SIGNATURES = {
     "dyn_debug_tile_image_off": (_sz, [C.c_longlong, _i, _i]),
     "dyn_linear_tc_packed_bytes": (_sz, [_i, _i]),
     "dyn_linear_tc": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    "dyn_composite_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "dyn_project_gather_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dyn_encoder_param_count": (_sz, []),
     "dyn_encoder_workspace_bytes": (_sz, [_i, _i, _i]),
     "dyn_encoder_forward": (_i, [_vp, _sz, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

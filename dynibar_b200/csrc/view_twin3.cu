@@ -817,30 +817,34 @@ int launch_view_twin3(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
   a.wimg = n->twin3.img;
   a.chunks = n->twin3.tab;
   a.nchunks = n->twin3.nchunks;
-  { const char* e = getenv("DYN_ABLATE"); a.ablate = e ? atoi(e) : 0; }
-  int dev = 0, sms = 148;
-  DYN_CUDA(cudaGetDevice(&dev));
-  DYN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // one-time set-up (profiling knob DYN_ABLATE, SM count, dynamic shared-memory opt-in of every instantiation)
+  static int ablate = -1, sms = 0;
+  if (ablate < 0) {
+    const char* e = getenv("DYN_ABLATE");
+    int dev = 0;
+    DYN_CUDA(cudaGetDevice(&dev));
+    DYN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+#define PREP_VT(VPV, STV) \
+    DYN_CUDA(cudaFuncSetAttribute(view_twin3_kernel<VPV, STV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, twin_smem(1)))
+    PREP_VT(8, true); PREP_VT(16, true); PREP_VT(8, false); PREP_VT(16, false);
+#undef PREP_VT
+    ablate = e ? atoi(e) : 0;
+  }
+  a.ablate = ablate;
   const int VP = V <= 8 ? 8 : 16;
-  const int nt = 1;
-  const long long rows = 128LL * nt;
-  const long long n_iter = (a.P * VP + rows - 1) / rows;
-  const long long slots = (long long)sms * (nt == 1 ? 2 : 1);
+  const long long n_iter = (a.P * VP + 127) / 128;
+  const long long slots = 2LL * sms;
   const int grid = (int)(n_iter < slots ? n_iter : slots);
   if (grid == 0) return DYN_OK;
   const bool st_net = n->kind == DYN_NET_STATIC;
   ProfScope prof(st_net ? PROF_VIEW_ST : PROF_VIEW_DY, st);
-#define LAUNCH_VT(VPV, STV, NTV)                                                                 \
-  do {                                                                                           \
-    DYN_CUDA(cudaFuncSetAttribute(view_twin3_kernel<VPV, STV, NTV>,                               \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, twin_smem(NTV))); \
-    view_twin3_kernel<VPV, STV, NTV><<<grid, NTV * 256 + 64, twin_smem(NTV), st>>>(a);            \
-  } while (0)
-#define LAUNCH_VT2(VPV, STV) LAUNCH_VT(VPV, STV, 1)
-  if (st_net) { if (VP == 8) LAUNCH_VT2(8, true); else LAUNCH_VT2(16, true); }
-  else { if (VP == 8) LAUNCH_VT2(8, false); else LAUNCH_VT2(16, false); }
-#undef LAUNCH_VT2
-#undef LAUNCH_VT
+  if (st_net) {
+    if (VP == 8) view_twin3_kernel<8, true, 1><<<grid, 320, twin_smem(1), st>>>(a);
+    else view_twin3_kernel<16, true, 1><<<grid, 320, twin_smem(1), st>>>(a);
+  } else {
+    if (VP == 8) view_twin3_kernel<8, false, 1><<<grid, 320, twin_smem(1), st>>>(a);
+    else view_twin3_kernel<16, false, 1><<<grid, 320, twin_smem(1), st>>>(a);
+  }
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }

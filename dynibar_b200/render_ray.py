@@ -12,7 +12,10 @@ kernels have no backward yet, so `requires_grad` inputs raise.
 """
 
 from collections import OrderedDict
+import contextlib
 import ctypes as C
+import os
+import threading
 import weakref
 
 import torch
@@ -22,16 +25,41 @@ from dynibar_b200 import weights as _weights
 from dynibar_b200._lib import lib, ptr, f32c, check, stream, dev_of, Args
 from dynibar_b200.projection import project_gather
 
-# GEMM precision of the network kernels: _lib.PREC_FP32 (SIMT parity mode) or
-# _lib.PREC_BF16 (tcgen05, bf16 operands / fp32 accumulate).
-PRECISION = _lib.PREC_FP32
+# GEMM precision of the network kernels: "bf16" = tcgen05 (bf16 operands / fp32 accumulate and statistics; the
+# production mode and the default), "fp32" = SIMT everywhere (parity mode).  Three ways to choose, innermost wins:
+# the `precision=` argument of render_rays_mv / render_rays_mono (per call), `precision_scope(name)` (per
+# thread, a context manager), `set_precision(name)` / the DYNIBAR_B200_PRECISION environment variable (process
+# default).
+_PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+PRECISION = _PREC[os.environ.get("DYNIBAR_B200_PRECISION", "bf16")]
+_tls = threading.local()
 # DYN_PREC_BF16: use the fused per-view kernels (False = staged tensor-core layers)
 USE_FUSED = True
 
 
 def set_precision(name):
+  """Process-wide default ("fp32" | "bf16")."""
   global PRECISION
-  PRECISION = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[name]
+  PRECISION = _PREC[name]
+
+
+@contextlib.contextmanager
+def precision_scope(name):
+  """Precision of every library call made by this thread inside the block (None = leave unchanged)."""
+  if name is None:
+    yield
+    return
+  prev = getattr(_tls, "override", None)
+  _tls.override = _PREC[name]
+  try:
+    yield
+  finally:
+    _tls.override = prev
+
+
+def _prec():
+  o = getattr(_tls, "override", None)
+  return PRECISION if o is None else o
 
 
 def _no_grad_only(*tensors):
@@ -122,7 +150,7 @@ def motion_mlp_forward(module, xyzt):
   ws = _lib.workspace.get(nbytes, dev)
   A = Args()
   with torch.cuda.device(dev):
-    check(lib.dyn_motion_mlp(net.handle, ptr(x), N, ptr(out), ws.data_ptr(), nbytes, PRECISION,
+    check(lib.dyn_motion_mlp(net.handle, ptr(x), N, ptr(out), ws.data_ptr(), nbytes, _prec(),
                              stream()))
   div = float(getattr(_weights.de_parallel(module), "sf_mag_div", 1.0))
   if div != 1.0:
@@ -141,7 +169,7 @@ def motion_coefficients(module, pts, t):
   A = Args()
   with torch.cuda.device(dev):
     check(lib.dyn_motion_coeffs(net.handle, A(pts), float(t), R, S, ptr(out),
-                                ws.data_ptr(), nbytes, PRECISION, stream()))
+                                ws.data_ptr(), nbytes, _prec(), stream()))
   div = float(getattr(_weights.de_parallel(module), "sf_mag_div", 1.0))
   if div != 1.0:  # MotionMLP.forward divides its output (mlp_network.py:617)
     out = out / div
@@ -232,7 +260,7 @@ def net_dynamic_forward(module, pts, rgb_feat, ray_dir, mask, time):
   with torch.cuda.device(dev):
     check(lib.dyn_net_dynamic(net.handle, A(pts), A(rgb_feat), A(ray_dir),
                               A(mask), t, R, S, V, ptr(raw), ws.data_ptr(), nbytes,
-                              PRECISION, stream()))
+                              _prec(), stream()))
   return raw
 
 
@@ -249,7 +277,7 @@ def net_static_forward(module, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask
   with torch.cuda.device(dev):
     check(lib.dyn_net_static(net.handle, A(pts), A(ref_rays), A(src_rays),
                              A(rgb_feat), A(ray_diff), A(mask), R, S, V,
-                             ptr(raw), ws.data_ptr(), nbytes, PRECISION, stream()))
+                             ptr(raw), ws.data_ptr(), nbytes, _prec(), stream()))
   return raw
 
 
@@ -488,7 +516,7 @@ def _render_pass(ray_batch, feat_dy, feat_st, pts, z, s, t, frame_idx, offsets, 
   ray_dir = ref_plucker[:, :3]  # == F.normalize(ray_d) (render_ray.py:455)
   coeff = motion_coefficients(motion, pts, t)
   seq = displaced_points(pts, coeff, basis, frame_idx, offsets, num_vv)
-  fused = (PRECISION == _lib.PREC_BF16 and USE_FUSED and ray_batch["src_cameras"].shape[1] <= 16
+  fused = (_prec() == _lib.PREC_BF16 and USE_FUSED and ray_batch["src_cameras"].shape[1] <= 16
            and ray_batch["static_src_cameras"].shape[1] <= 16)
   if fused:
     # gather + per-view MLP chain + pooling in one tcgen05 kernel per branch: the
@@ -527,7 +555,7 @@ def _render_pass(ray_batch, feat_dy, feat_st, pts, z, s, t, frame_idx, offsets, 
 def render_rays_mv(frame_idx, time_embedding, time_offset, ray_batch, model, projector,
                    coarse_featmaps, fine_featmaps, N_samples, args, inv_uniform=False,
                    N_importance=0, raw_noise_std=0.0, det=False, white_bkgd=False, is_train=True,
-                   jitter=None, u=None):
+                   jitter=None, u=None, precision=None):
   """Coarse + fine rendering for the Nvidia multi-view benchmark
   (render_ray.py:600-867).  Extra keyword-only inputs `jitter` / `u` carry the
   random draws of :119 / :34 when det=False (drawn with torch.rand if None).
@@ -535,7 +563,7 @@ def render_rays_mv(frame_idx, time_embedding, time_offset, ray_batch, model, pro
   outputs_fine_ref_dy, outputs_fine_anchor(None), outputs_fine_anchor_dy(None)."""
   assert N_importance > 0  # render_ray.py:787
   _refuse_training(model, coarse_featmaps, fine_featmaps)
-  with torch.no_grad():
+  with torch.no_grad(), precision_scope(precision):
     t = _scalar(time_embedding[0].float())
     offs = [int(o) for o in time_offset[0]]
     fidx = int(frame_idx[0])
@@ -562,12 +590,12 @@ def render_rays_mv(frame_idx, time_embedding, time_offset, ray_batch, model, pro
 
 def render_rays_mono(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, projector,
                      N_samples, args, inv_uniform=False, N_importance=0, raw_noise_std=0.0,
-                     det=False, white_bkgd=False, is_train=True, num_vv=2, jitter=None):
+                     det=False, white_bkgd=False, is_train=True, num_vv=2, jitter=None, precision=None):
   """Coarse-only rendering for monocular video (render_ray.py:870-1277), including the
   cross-time branch (:1099-1270) when is_train=True.  Forward only: the kernels have no
   backward yet, so everything runs under no_grad (training needs SURVEY 8(f) f2)."""
   _refuse_training(model, featmaps)
-  with torch.no_grad():
+  with torch.no_grad(), precision_scope(precision):
     t = _scalar(time_embedding[0].float())
     ray_batch, hb = _with_host_copies(ray_batch, model, ("trajectory_basis",))
     basis = hb["trajectory_basis"]
@@ -602,7 +630,7 @@ def _cross_time(ray_batch, feat_anchor, pts, z, aux, ref_idx, anc_idx, t_anc, an
   pts_traj_ref = displaced_points(pts, coeff, basis, ref_idx, [ro for _, ro in keep])
   cam = ray_batch["camera"]
   V_a = ray_batch["anchor_src_cameras"].shape[1]
-  if PRECISION == _lib.PREC_BF16 and USE_FUSED and V_a <= 16:
+  if _prec() == _lib.PREC_BF16 and USE_FUSED and V_a <= 16:
     raw_a, m_a = net_dynamic_fused(model.net_coarse_dy, pts_anchor, seq_a, aux["ray_dir"], cam,
                                    ray_batch["anchor_src_rgbs"], ray_batch["anchor_src_cameras"],
                                    featmaps_channels_last(feat_anchor), t_anc)

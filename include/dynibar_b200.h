@@ -53,6 +53,8 @@ int dyn_device_sm_count(void);
 /* Kernels launched by this library since load (or the last reset). */
 unsigned long long dyn_launch_count(int reset);
 
+/* (debug / measurement hooks below -- dyn_profile_*, dyn_debug_*, dyn_launch_count -- keep process-global
+ * state and are NOT thread-safe; the entry points of the path itself only touch caller-owned buffers.) */
 /* Optional device timing of the big kernels (CUDA events on the launching
  * stream, recorded inside the library around each launch).  Classes: 0 fused
  * static per-view stage, 1 fused dynamic per-view stage, 2 MotionMLP, 3 point
@@ -233,6 +235,22 @@ int dyn_flow_sceneflow(const float* weights, const float* pts_seq,
                        const float* coeff, const float* basis, int T, int nb,
                        int frame_idx, int sf_k, int n_flow, int R, int S,
                        float* flows, float* exp_sf, void* stream);
+
+/* ---- f2 (first slice): backward of the two non-MLP ends of the path -------------------------
+ * dyn_composite_backward: raw2outputs (render_ray.py:214-330).  g_rays [R,11] = d/d(rgb, rgb_static,
+ * rgb_dy, depth, mask(ignored)), g_samples [5,R,S] = d/d(alpha_dy, weights_dy, weights_st, alpha,
+ * weights) or NULL -> g_raw_dy, g_raw_st [R,S,4].  S <= 256.
+ * dyn_project_gather_backward: compute_with_motions (projection.py:103-176).  g_rgb_feat [R,S,V,3+C]
+ * -> g_featmaps [V,C,h,w] (reference layout; zeroed here, atomically accumulated) and / or g_xyz [V,R,S,3]
+ * (either may be NULL).  xyz may be NULL (every view uses xyz_st). */
+int dyn_composite_backward(const float* raw_dy, const float* raw_st, const float* z_vals,
+                           const float* g_rays, const float* g_samples, int R, int S,
+                           float* g_raw_dy, float* g_raw_st, void* stream);
+int dyn_project_gather_backward(const float* xyz_st, const float* xyz, const float* src_rgbs,
+                                const float* src_cams, const float* featmaps,
+                                const float* g_rgb_feat, int V, int R, int S, int H, int W,
+                                int C, int h, int w, float* g_featmaps, float* g_xyz,
+                                void* stream);
 
 /* ---- f1: 2-D feature encoder, ResNet.forward as the reference runs it (feature_network.py:302-311) ----
  * conv 7x7 stride 2 (reflect) -> InstanceNorm -> ReLU -> layer1 (3 BasicBlocks, the first with stride 2)

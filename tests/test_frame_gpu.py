@@ -23,6 +23,13 @@ DEV = "cuda:0"
 _dev = lambda x: synthetic.to_device(x, DEV)
 
 
+@pytest.fixture(autouse=True)
+def _fp32_parity_mode():
+  from dynibar_b200 import render_ray as rr
+  with rr.precision_scope("fp32"):
+    yield
+
+
 def _fixture(name):
   return torch.load(os.path.join(os.path.dirname(__file__), "golden", name + ".pt"), weights_only=False)
 

@@ -13,11 +13,12 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(scope="module")
+@pytest.fixture
 def rr():
+  """every test of this module runs in the fp32 parity mode (the library default is bf16)"""
   from dynibar_b200 import render_ray
-  render_ray.set_precision("fp32")
-  return render_ray
+  with render_ray.precision_scope("fp32"):
+    yield render_ray
 
 
 def _dev(x):

@@ -81,18 +81,16 @@ def test_bf16_mode_end_to_end(golden, name):
                                 is_train=False)
       key = "outputs_fine_ref"
   m = synthetic.model_to(model, DEV)
-  rr.set_precision("bf16")
-  try:
-    if cfg["mono"]:
-      got = rr.render_rays_mono(frame, t, offs, d(batch), m, d(feat_c), Projector(DEV),
-                                cfg["N_samples"], args, inv_uniform=True, det=True,
-                                is_train=cfg.get("anchor_offset") is not None, num_vv=cfg["num_vv"])
-    else:
-      got = rr.render_rays_mv(frame, t, offs, d(batch), m, Projector(DEV), d(feat_c), d(feat_f),
-                              cfg["N_samples"], args, inv_uniform=True,
-                              N_importance=cfg["N_importance"], det=True, is_train=False)
-  finally:
-    rr.set_precision("fp32")
+  # per-call precision argument (innermost of the three ways to choose the mode)
+  if cfg["mono"]:
+    got = rr.render_rays_mono(frame, t, offs, d(batch), m, d(feat_c), Projector(DEV),
+                              cfg["N_samples"], args, inv_uniform=True, det=True,
+                              is_train=cfg.get("anchor_offset") is not None, num_vv=cfg["num_vv"],
+                              precision="bf16")
+  else:
+    got = rr.render_rays_mv(frame, t, offs, d(batch), m, Projector(DEV), d(feat_c), d(feat_f),
+                            cfg["N_samples"], args, inv_uniform=True,
+                            N_importance=cfg["N_importance"], det=True, is_train=False, precision="bf16")
   g, w = got[key], want[key]
   # only the stress rigs put samples on in-bounds discontinuities (util.assert_close_frac)
   bad = 0.02 if cfg.get("stress") else 1e-3
@@ -143,7 +141,7 @@ def test_bf16_mode_against_oracle_at_benchmark_shapes(name):
                               cfg["N_samples"], args, inv_uniform=True, N_importance=cfg["N_importance"],
                               det=True, is_train=False)
   finally:
-    rr.set_precision("fp32")
+    rr.set_precision("bf16")
   for key in keys:
     g, w = got[key], want[key]
     for kk in ("rgb", "weights", "depth"):
@@ -277,7 +275,7 @@ def _run_mode(cfg, precision, mono=False):
                              cfg["N_samples"], args, inv_uniform=True, N_importance=cfg["N_importance"],
                              det=True, is_train=False)
   finally:
-    rr.set_precision("fp32")
+    rr.set_precision("bf16")
 
 
 def test_wide_view_counts_use_16_slot_kernels():
@@ -335,7 +333,7 @@ def test_ragged_and_empty_ray_batches(rays):
     got = rr.render_rays_mv(frame, t, offs, d(batch), m, Projector(DEV), d(feat_c), d(feat_f), 32, args,
                             inv_uniform=True, N_importance=32, det=True, is_train=False)["outputs_fine_ref"]
   finally:
-    rr.set_precision("fp32")
+    rr.set_precision("bf16")
   assert got["rgb"].shape == (rays, 3) and got["weights"].shape == (rays, 64)
   if rays:
     assert_close_frac("rgb", got["rgb"], want["rgb"], rtol=0, atol=2e-3, max_bad_frac=0.03)
@@ -360,7 +358,7 @@ def test_bf16_full_size_properties():
       return rr.render_rays_mv(frame, t, offs, bb, m, Projector(DEV), fc, ff, 64, args, inv_uniform=True,
                                N_importance=64, det=True, is_train=False)["outputs_fine_ref"]
     finally:
-      rr.set_precision("fp32")
+      rr.set_precision("bf16")
 
   full = run(b, "bf16")
   perm = torch.randperm(8192, device=DEV)
