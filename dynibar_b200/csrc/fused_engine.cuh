@@ -35,36 +35,6 @@ __device__ __forceinline__ float elu_log2(float x2) {
   const float e = ex2f(x2);
   return x2 > 0.f ? x2 : fmaf(e, 1.4426950408889634f, -1.4426950408889634f);
 }
-// 2^x for x <= 0 on the FMA / ALU pipes only (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-4
-// Taylor polynomial of 2^f (relative error < 5e-5, far below the bf16 rounding of the result), exponent added
-// to the float's bit pattern.  The XU pipe (16 lanes/clk/SM) is the contended unit of the ELU epilogues: when
-// every 4th activation takes this path, XU and issue slots balance (profiles/r02_kernels.md).
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.f);
-  const float r = x + 12582912.f;            // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float f = x - (r - 12582912.f);
-  float p = fmaf(f, 0.009618129f, 0.055504109f);
-  p = fmaf(p, f, 0.240226507f);
-  p = fmaf(p, f, 0.693147181f);
-  p = fmaf(p, f, 1.f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
-}
-// exp2 by MUFU (kPoly = false) or by ex2_poly on a negative-clamped argument (only the x <= 0 branch of the
-// ELU uses the result)
-template <bool kPoly>
-__device__ __forceinline__ float ex2_sel(float x) {
-  return kPoly ? ex2_poly(fminf(x, 0.f)) : ex2f(x);
-}
-template <bool kPoly>
-__device__ __forceinline__ float elu_log2_t(float x2) {
-  const float e = ex2_sel<kPoly>(x2);
-  return x2 > 0.f ? x2 : fmaf(e, 1.4426950408889634f, -1.4426950408889634f);
-}
-template <bool kPoly>
-__device__ __forceinline__ float elu_from_log2_t(float x2) {
-  const float e = ex2_sel<kPoly>(x2);
-  return x2 > 0.f ? x2 * 0.6931471805599453f : e - 1.f;
-}
 // ELU in true units from an accumulator on the exp2 scale (x2 = log2(e) * x): 4 instructions
 __device__ __forceinline__ float elu_from_log2(float x2) {
   const float e = ex2f(x2);

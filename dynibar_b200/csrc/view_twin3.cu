@@ -79,7 +79,7 @@ __device__ __forceinline__ void pe_comp(float x, float* o) {
 }
 
 // layers whose bias rides in the MMA and whose accumulator is on the exp2 scale (F1, F3)
-template <int N, bool POLY = false>
+template <int N>
 __device__ __forceinline__ void elu_log2_block_to_A(uint8_t* arow, uint32_t tacc, int col0) {
 #pragma unroll 1
   for (int cb = 0; cb < N; cb += 32) {
@@ -87,7 +87,7 @@ __device__ __forceinline__ void elu_log2_block_to_A(uint8_t* arow, uint32_t tacc
     tmem_ld32(tacc + col0 + cb, acc);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = ((i & 3) == 3) ? elu_log2_t<POLY>(acc[i]) : elu_log2(acc[i]);
+    for (int i = 0; i < 32; ++i) acc[i] = elu_log2(acc[i]);
 #pragma unroll
     for (int g = 0; g < 4; ++g) store8(arow, col0 + cb + 8 * g, acc + 8 * g);
   }
@@ -107,10 +107,7 @@ __device__ __forceinline__ void elu_block_to_A(uint8_t* arow, uint32_t tacc, int
   }
 }
 
-// POLY: every 4th ELU evaluates its exponential on the FMA pipe (fused_engine.cuh: ex2_poly) instead of MUFU
-#define ELU_L2(i, x) (((i) & 3) == 3 ? elu_log2_t<POLY>(x) : elu_log2(x))
-#define ELU_FL2(i, x) (((i) & 3) == 3 ? elu_from_log2_t<POLY>(x) : elu_from_log2(x))
-template <int VP, bool ST, int NT, bool POLY>
+template <int VP, bool ST, int NT>
 __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
     view_twin3_kernel(const __grid_constant__ ViewFusedArgs a) {
   constexpr int ROWS = 128 * NT;          // rows per iteration
@@ -162,12 +159,6 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
 
   const long long n_rows = a.P * VP;
   const int n_iter = (int)((n_rows + ROWS - 1) / ROWS);
-  if ((a.ablate & 16) && (int)blockIdx.x >= (int)(gridDim.x / 2)) {
-    // experiment: start the second CTA of every SM half an iteration late so that the two CTAs' MUFU-heavy
-    // epilogues and MMA rounds interleave instead of coinciding
-    const long long t0 = clock64();
-    while (clock64() - t0 < (long long)(a.ablate >> 8)) {}
-  }
 
   if (warp == W_PROD) {
     if ((tid & 31) < a.producers)
@@ -390,7 +381,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
         TS();  // 3: F1 acc ready
         tc_fence_after_sync();
-        elu_log2_block_to_A<128, POLY>(arow, tacc, 128 * tw);
+        elu_log2_block_to_A<128>(arow, tacc, 128 * tw);
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(bar_aready(bar0, bt, RING));
@@ -492,7 +483,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         const int col = 32 * ((j < 2 ? 4 : 0) + 2 * (j & 1) + tw);
-        elu_log2_block_to_A<32, POLY>(arow, tacc, col);
+        elu_log2_block_to_A<32>(arow, tacc, col);
         if (j & 1) {
           fence_proxy_async_smem();
           tc_fence_before_sync();
@@ -514,7 +505,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         tmem_ld32(tacc + 128 + cb, acc);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = ELU_FL2(i, acc[i]);
+        for (int i = 0; i < 32; ++i) acc[i] = elu_from_log2(acc[i]);
 #pragma unroll
         for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
         fence_proxy_async_smem();
@@ -537,7 +528,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            acc[i] = ELU_L2(i, fmaf(acc[i], w1, cst[T_B5 + cb + i]));  // log2(e) * ELU(w1 (W x) + b)
+            acc[i] = elu_log2(fmaf(acc[i], w1, cst[T_B5 + cb + i]));  // log2(e) * ELU(w1 (W x) + b)
             part = fmaf(acc[i], cst[T_W6V + cb + i], part);
           }
 #pragma unroll
@@ -574,8 +565,8 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           uint32_t o[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float lo = __uint_as_float(u[k] << 16) + elu_from_log2(acc[8 * i + 2 * k]);  // (k & 1) lanes below
-            const float hi = __uint_as_float(u[k] & 0xffff0000u) + ELU_FL2(2 * k + 1, acc[8 * i + 2 * k + 1]);
+            const float lo = __uint_as_float(u[k] << 16) + elu_from_log2(acc[8 * i + 2 * k]);
+            const float hi = __uint_as_float(u[k] & 0xffff0000u) + elu_from_log2(acc[8 * i + 2 * k + 1]);
             o[k] = pack_bf16x2(lo, hi);
           }
           pk[i] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -610,7 +601,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            part = fmaf(ELU_L2(i, fmaf(acc[i], vis1, cst[T_B7 + cb + i])), cst[T_W8 + cb + i], part);
+            part = fmaf(elu_log2(fmaf(acc[i], vis1, cst[T_B7 + cb + i])), cst[T_W8 + cb + i], part);
         }
         xch7[tw * 128 + t] = part;
       }
@@ -834,8 +825,7 @@ int launch_view_twin3(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
     DYN_CUDA(cudaGetDevice(&dev));
     DYN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 #define PREP_VT(VPV, STV) \
-    DYN_CUDA(cudaFuncSetAttribute(view_twin3_kernel<VPV, STV, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, twin_smem(1))); \
-    DYN_CUDA(cudaFuncSetAttribute(view_twin3_kernel<VPV, STV, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, twin_smem(1)))
+    DYN_CUDA(cudaFuncSetAttribute(view_twin3_kernel<VPV, STV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, twin_smem(1)))
     PREP_VT(8, true); PREP_VT(16, true); PREP_VT(8, false); PREP_VT(16, false);
 #undef PREP_VT
     ablate = e ? atoi(e) : 0;
@@ -848,14 +838,13 @@ int launch_view_twin3(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
   if (grid == 0) return DYN_OK;
   const bool st_net = n->kind == DYN_NET_STATIC;
   ProfScope prof(st_net ? PROF_VIEW_ST : PROF_VIEW_DY, st);
-#define LAUNCH_VT3(VPV, STV)                                                                            \
-  do {                                                                                                  \
-    if (a.ablate & 32) view_twin3_kernel<VPV, STV, 1, true><<<grid, 320, twin_smem(1), st>>>(a);        \
-    else view_twin3_kernel<VPV, STV, 1, false><<<grid, 320, twin_smem(1), st>>>(a);                      \
-  } while (0)
-  if (st_net) { if (VP == 8) LAUNCH_VT3(8, true); else LAUNCH_VT3(16, true); }
-  else { if (VP == 8) LAUNCH_VT3(8, false); else LAUNCH_VT3(16, false); }
-#undef LAUNCH_VT3
+  if (st_net) {
+    if (VP == 8) view_twin3_kernel<8, true, 1><<<grid, 320, twin_smem(1), st>>>(a);
+    else view_twin3_kernel<16, true, 1><<<grid, 320, twin_smem(1), st>>>(a);
+  } else {
+    if (VP == 8) view_twin3_kernel<8, false, 1><<<grid, 320, twin_smem(1), st>>>(a);
+    else view_twin3_kernel<16, false, 1><<<grid, 320, twin_smem(1), st>>>(a);
+  }
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }

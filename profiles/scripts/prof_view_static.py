@@ -4,8 +4,6 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT,'tests'))
 import torch
 from dynibar_b200 import synthetic, render_ray as rr
 DEV='cuda:0'
-from dynibar_b200 import _lib
-_lib.lib.dyn_debug_set_view_kernel(int(sys.argv[1]) if len(sys.argv) > 1 else -1)
 R,S=512,128
 batch, feat_c, feat_f, frame, t, offs = synthetic.make_scene(rays=R, seed=0)
 model, args = synthetic.make_model(64,64)
