@@ -35,7 +35,7 @@ KERNEL_CLASSES = ["view_static", "view_dynamic", "motion", "point1", "point2", "
                   "gather"]
 # DRAM bytes per (point, view) row of the static per-view kernel from the committed ncu capture
 # (dram__bytes_read.sum + dram__bytes_write.sum per launch / rows); see profiles/
-NCU_DRAM_BYTES_PER_ROW = {"view_static": 291.5}  # profiles/r01_view_twin_ncu.md (152.8 MB / 524 288 rows)
+NCU_DRAM_BYTES_PER_ROW = {"view_static": 298.0}  # profiles/r02_view_twin_ncu.md (156.2 MB / 524 288 rows)
 
 WORKLOAD = dict(H=288, W=512, V_dy=8, V_st=8, N_samples=64, N_importance=64, chunk=8192, seed=0)
 METRIC = "rays/sec (64+64 samples x 8 src views)"

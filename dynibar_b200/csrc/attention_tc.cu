@@ -12,6 +12,8 @@
 // O (fp32, TMEM columns [128,256)) is written to global at the end, again as a bf16 tile image.
 #include "nets.cuh"
 #include "tc.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace dyn {
 
@@ -217,6 +219,196 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
   }
 }
 
+
+// ---- S = 64 or 128: the bench shapes -------------------------------------------------------------------
+// Same data flow as attention_tc_kernel<true>, specialised so that a thread's keys are exactly NB whole
+// 32-column TMEM blocks (twin tw of row r owns keys [ray_lo + 32 NB tw, + 32 NB)):
+//  * logits are read from TMEM once and stay in registers between the max and the exp pass;
+//  * no per-key range tests; the 1/sqrt(32) scale, log2(e) and the max shift are one FFMA in front of ex2;
+//  * the columns of P that belong to the tile's other ray (S = 64) are zero for every head and tile: they
+//    are cleared once per CTA;
+//  * K, Q_0 and V of the CTA's next tile are requested as soon as the last QK^T / PV of the current tile
+//    has retired, so the loads overlap the last softmax and the write-out.
+template <int NB>
+__global__ void __launch_bounds__(256, 2)
+attention_twin_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K,
+                      const __nv_bfloat16* __restrict__ V, const float* __restrict__ nvalid, long long P,
+                      __nv_bfloat16* __restrict__ O) {
+  constexpr int S = 64 * NB;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* kt = smem;
+  uint8_t* vt = smem + kTile;
+  uint8_t* pt = smem + 2 * kTile;
+  uint8_t* qt = smem + 3 * kTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kTile + kQSlice);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_s = smem_u32(bars), bar_o = smem_u32(bars + 1);
+  const uint32_t bar_k = smem_u32(bars + 2), bar_q = smem_u32(bars + 3), bar_v = smem_u32(bars + 5);
+  if (tid == 0) {
+    mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_k, 1); mbar_init(bar_q, 1); mbar_init(bar_v, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tacc = tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), 0);
+
+  const int r = tid & 127, tw = tid >> 7, rw = warp & 3;
+  const size_t roff = (size_t)(r >> 3) * 128 + (r & 7) * 16;
+  const int ray_lo = (r / S) * S;
+  const int k_lo = ray_lo + tw * 32 * NB;
+  float* den_part = reinterpret_cast<float*>(bars + 8);  // [2][128][4]
+  float* max_part = den_part + 2 * 128 * 4;              // [2][128]
+  uint32_t ph_s = 0, ph_o = 0, ph_k = 0, ph_q = 0, ph_v = 0;
+  const uint8_t* qimg = reinterpret_cast<const uint8_t*>(Q);
+  const uint8_t* kimg = reinterpret_cast<const uint8_t*>(K);
+  const uint8_t* vimg = reinterpret_cast<const uint8_t*>(V);
+
+  if (NB == 1) {  // keys of the other ray of the tile: P = 0, never rewritten
+#pragma unroll
+    for (int kg = 0; kg < 16; ++kg)
+      if ((kg * 8 < ray_lo || kg * 8 >= ray_lo + S) && (kg & 1) == tw)
+        *reinterpret_cast<uint4*>(pt + roff + kg * 2048) = make_uint4(0u, 0u, 0u, 0u);
+  }
+
+  auto issue_qk = [&](int h) {
+    mbar_wait(bar_q, ph_q & 1); ++ph_q;
+    tc_fence_after_sync();
+    if (elect_one()) {
+      const uint32_t idesc = idesc_bf16_f32(128, 128);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma_bf16_ss(tmem_base, smem_desc(smem_u32(qt) + (2 * ks) * 2048u, 2048u, 128u),
+                    smem_desc(smem_u32(kt) + (4 * h + 2 * ks) * 2048u, 2048u, 128u), idesc, ks ? 1u : 0u);
+      mma_commit(bar_s);
+    }
+    __syncwarp();
+  };
+  auto load_q = [&](long long tile, int h) {
+    mbar_arrive_expect_tx(bar_q, (uint32_t)kQSlice);
+    bulk_g2s(smem_u32(qt), qimg + (size_t)tile * kTile + (size_t)h * kQSlice, (uint32_t)kQSlice, bar_q);
+  };
+  auto load_k = [&](long long tile) {
+    mbar_arrive_expect_tx(bar_k, (uint32_t)kTile);
+    bulk_g2s(smem_u32(kt), kimg + (size_t)tile * kTile, (uint32_t)kTile, bar_k);
+  };
+  auto load_v = [&](long long tile) {
+    mbar_arrive_expect_tx(bar_v, (uint32_t)kTile);
+    bulk_g2s(smem_u32(vt), vimg + (size_t)tile * kTile, (uint32_t)kTile, bar_v);
+  };
+
+  const long long n_tiles = (P + 127) / 128;
+  if (tid == 0 && (long long)blockIdx.x < n_tiles) {
+    load_k(blockIdx.x);
+    load_q(blockIdx.x, 0);
+    load_v(blockIdx.x);
+  }
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row = tile * 128 + r;
+    const long long next = tile + gridDim.x;
+    const bool ok = row < P;
+    const bool q_valid = ok && nvalid[row] > 1.f;
+    // exp(l / sqrt(32) - max) = 2^(l sc - max sc); a query row without two valid views attends uniformly
+    const float sc = q_valid ? 0.17677669529663687f * 1.4426950408889634f : 0.f;
+    if (warp == 0) {
+      mbar_wait(bar_k, ph_k & 1); ++ph_k;
+      issue_qk(0);
+    }
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      mbar_wait(bar_s, ph_s & 1);
+      ++ph_s;
+      tc_fence_after_sync();
+      if (tid == 0) {
+        if (h < 3) load_q(tile, h + 1);  // Q_h has been consumed
+        else if (next < n_tiles) { load_k(next); load_q(next, 0); }  // and so has K
+      }
+      float l[NB][32];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) tmem_ld32(tacc + k_lo + 32 * b, l[b]);
+      tmem_wait_ld();
+      float mx = l[0][0];
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, l[b][i]);
+      max_part[tw * 128 + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + rw) : "memory");
+      mx = fmaxf(mx, max_part[(tw ^ 1) * 128 + r]);
+      const float sh = mx * sc;
+      // previous head's P V must be done before P is overwritten
+      if (h > 0) { mbar_wait(bar_o, ph_o & 1); ++ph_o; }
+      float den = 0.f;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(l[b][i], sc, -sh)));
+          l[b][i] = e;
+          den += e;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 q;
+          q.x = pack_bf16x2(l[b][8 * g], l[b][8 * g + 1]); q.y = pack_bf16x2(l[b][8 * g + 2], l[b][8 * g + 3]);
+          q.z = pack_bf16x2(l[b][8 * g + 4], l[b][8 * g + 5]); q.w = pack_bf16x2(l[b][8 * g + 6], l[b][8 * g + 7]);
+          *reinterpret_cast<uint4*>(pt + roff + ((k_lo >> 3) + 4 * b + g) * 2048) = q;
+        }
+      }
+      den_part[(tw * 128 + r) * 4 + h] = den;  // 1 / sum applied when O is written out
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();  // P complete; every thread is done reading logits_h
+      if (warp == 0) {
+        if (h == 0) { mbar_wait(bar_v, ph_v & 1); ++ph_v; }
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t idesc = idesc_bf16_f32_bmn(128, 32);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            mma_bf16_ss(tmem_base + 128 + 32 * h, smem_desc(smem_u32(pt) + ks * 4096u, 2048u, 128u),
+                        smem_desc(smem_u32(vt) + (4 * h) * 2048u + ks * 256u, 128u, 2048u), idesc,
+                        ks ? 1u : 0u);
+          mma_commit(bar_o);
+        }
+        __syncwarp();
+        if (h < 3) issue_qk(h + 1);
+      }
+    }
+    mbar_wait(bar_o, ph_o & 1);
+    ++ph_o;
+    tc_fence_after_sync();
+    if (tid == 0 && next < n_tiles) load_v(next);  // the last P V has retired: V is free
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      float o[16];
+      tmem_ld16(tacc + 128 + 32 * h + 16 * tw, o);
+      tmem_wait_ld();
+      if (ok) {
+        const float inv = 1.f / (den_part[r * 4 + h] + den_part[(128 + r) * 4 + h]);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(O) + (size_t)tile * kTile + (size_t)(4 * h + 2 * tw) * 2048 +
+                       (size_t)r * 16;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          *reinterpret_cast<uint4*>(dst + i * 2048) = make_uint4(pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv),
+                              pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
+                              pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv),
+                              pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+      }
+    }
+    tc_fence_before_sync();
+    __syncthreads();  // P, den_part and TMEM are reused by the next iteration
+  }
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 }  // namespace
 
 bool attention_tc_supported(int S) { return S >= 1 && S <= 128 && (128 % S) == 0; }
@@ -231,7 +423,16 @@ int launch_attention_tc(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __
   const int grid = (int)(n_tiles < 2 * sms ? n_tiles : 2 * sms);
   const int smem = kSmemAttn;
   ProfScope prof(PROF_ATTENTION, st);
-  if (S % 64 == 0) {  // twin warps
+  static const bool generic = getenv("DYN_ATTENTION") && !strcmp(getenv("DYN_ATTENTION"), "generic");
+  if ((S == 64 || S == 128) && !generic) {
+    if (S == 64) {
+      DYN_CUDA(cudaFuncSetAttribute(attention_twin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attention_twin_kernel<1><<<grid, 256, smem, st>>>(Q, K, V, nvalid, P, O);
+    } else {
+      DYN_CUDA(cudaFuncSetAttribute(attention_twin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attention_twin_kernel<2><<<grid, 256, smem, st>>>(Q, K, V, nvalid, P, O);
+    }
+  } else if (S % 64 == 0) {  // twin warps
     DYN_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attention_tc_kernel<true><<<grid, 256, smem, st>>>(Q, K, V, nvalid, P, S, O);
   } else {

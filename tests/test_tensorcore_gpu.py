@@ -189,13 +189,13 @@ def test_fused_view_stage_matches_staged(golden, name):
 
 
 @pytest.mark.parametrize("kind", ["dynamic", "static"])
-@pytest.mark.parametrize("S", [64, 128, 20, 16, 32])
-def test_fused_point_stage(kind, S):
+@pytest.mark.parametrize("S,R", [(64, 37), (128, 37), (20, 37), (16, 37), (32, 37), (64, 1301), (128, 701)])
+def test_fused_point_stage(kind, S, R):
   """point1 (geometry_fc, Q|K|V) -> attention -> point2 (fc + LayerNorm + heads) on random
-  pooled features, against the oracle's formulas with bf16 GEMM operands."""
+  pooled features, against the oracle's formulas with bf16 GEMM operands.  The two large R give every
+  CTA of the persistent kernels several tiles (the attention kernel's next-tile prefetch path)."""
   from dynibar_b200 import _lib, weights
   torch.manual_seed(S)
-  R = 37
   P = R * S
   model, args = synthetic.make_model(S, 0, mono=True, seed=4)
   mod = model.net_coarse_dy if kind == "dynamic" else model.net_coarse_st
