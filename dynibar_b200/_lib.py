@@ -71,6 +71,9 @@ SIGNATURES = {
     "dyn_debug_tile_image_off": (_sz, [C.c_longlong, _i, _i]),
     "dyn_linear_tc_packed_bytes": (_sz, [_i, _i]),
     "dyn_linear_tc": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    "dyn_motion_train_workspace_bytes": (_sz, [_i]),
+    "dyn_motion_mlp_train_forward": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "dyn_motion_mlp_backward": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp]),
     "dyn_composite_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "dyn_project_gather_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dyn_encoder_param_count": (_sz, []),

@@ -7,7 +7,10 @@ kernels of the two non-MLP ends of the path.
                         the source feature maps and the motion-displaced points (ray_diff and mask are detached /
                         non-differentiable, as in the reference).
 
-The MLP / ray-transformer backward is not built yet, so the orchestrators (`render_rays_*`) still refuse inputs
+  * `motion_mlp`        MotionMLP.forward (ibrnet/mlp_network.py:605-618): gradients w.r.t. every parameter of the
+                        module and w.r.t. the xyzt rows (fp32 GEMMs, csrc/motion_train.cu).
+
+The backward of the aggregation nets (per-view stage, ray transformer) is not built yet, so the orchestrators (`render_rays_*`) still refuse inputs
 that require grad; these functions are the tested building blocks of that step (tests/test_backward_gpu.py checks
 them against torch autograd through the oracle's restatement of the same functions).
 """
@@ -90,3 +93,50 @@ class _ProjectGather(torch.autograd.Function):
 def project_gather(xyz_st, xyz, query_camera, train_imgs, train_cameras, featmaps):
   """Differentiable Projector.compute_with_motions -> (rgb_feat, ray_diff, mask)."""
   return _ProjectGather.apply(xyz_st, xyz, featmaps, query_camera, train_imgs, train_cameras)
+
+
+class _MotionMLP(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, xyzt, module, *params):
+    from dynibar_b200 import weights
+    dev = dev_of(xyzt)
+    net = weights.packed_of(module, dev)
+    x = f32c(xyzt.detach()).reshape(-1, 4)
+    N = x.shape[0]
+    out = torch.empty(N, 3 * net.num_basis, device=dev)
+    nbytes = int(lib.dyn_motion_train_workspace_bytes(N))
+    saved = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+      check(lib.dyn_motion_mlp_train_forward(net.handle, ptr(x), N, ptr(out), saved.data_ptr(), nbytes, stream()))
+    ctx.net, ctx.ws, ctx.nbytes, ctx.x = net, saved, nbytes, x
+    ctx.in_shape = xyzt.shape
+    ctx.shapes = [p.shape for p in params]
+    return out.reshape(xyzt.shape[:-1] + (out.shape[-1],))
+
+  @staticmethod
+  def backward(ctx, g):
+    net, x = ctx.net, ctx.x
+    N = x.shape[0]
+    gc = f32c(g).reshape(N, -1)
+    d_params = torch.zeros(net.blob.numel(), device=x.device)
+    d_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+    with torch.cuda.device(x.device):
+      check(lib.dyn_motion_mlp_backward(net.handle, ptr(x), ptr(gc), N, ctx.ws.data_ptr(), ctx.nbytes,
+                                        ptr(d_params), ptr(d_x) if d_x is not None else None, stream()))
+    grads, o = [], 0
+    for shp in ctx.shapes:  # state_dict order == parameters() order == the blob's order (weights.py)
+      n = 1
+      for d in shp:
+        n *= d
+      grads.append(d_params[o:o + n].reshape(shp))
+      o += n
+    return (d_x.reshape(ctx.in_shape) if d_x is not None else None, None) + tuple(grads)
+
+
+def motion_mlp(module, xyzt):
+  """Differentiable MotionMLP.forward on [...,4] rows; honours `sf_mag_div` like render_ray.motion_mlp_forward."""
+  from dynibar_b200 import weights
+  m = weights.de_parallel(module)
+  out = _MotionMLP.apply(xyzt, module, *m.parameters())
+  div = float(getattr(m, "sf_mag_div", 1.0))
+  return out / div if div != 1.0 else out

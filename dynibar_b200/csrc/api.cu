@@ -288,6 +288,25 @@ int dyn_motion_mlp(dyn_net_t motion, const float* xyzt, int N, float* coeff, voi
                     (cudaStream_t)stream);
 }
 
+size_t dyn_motion_train_workspace_bytes(int N) { return motion_train_workspace(N < 0 ? 0 : N); }
+
+int dyn_motion_mlp_train_forward(dyn_net_t motion, const float* xyzt, int N, float* coeff, void* saved,
+                                 size_t saved_bytes, void* stream) {
+  DYN_CHECK_ARG(motion && motion->kind == DYN_NET_MOTION && N >= 0);
+  if (N == 0) return DYN_OK;
+  DYN_CHECK_ARG(xyzt && coeff && saved);
+  return motion_train_forward(motion, xyzt, N, coeff, saved, saved_bytes, (cudaStream_t)stream);
+}
+
+int dyn_motion_mlp_backward(dyn_net_t motion, const float* xyzt, const float* d_coeff, int N, void* saved,
+                            size_t saved_bytes, float* d_params, float* d_xyzt, void* stream) {
+  DYN_CHECK_ARG(motion && motion->kind == DYN_NET_MOTION && N >= 0);
+  if (N == 0) return DYN_OK;
+  DYN_CHECK_ARG(xyzt && d_coeff && saved && d_params);
+  return motion_train_backward(motion, xyzt, d_coeff, N, saved, saved_bytes, d_params, d_xyzt,
+                               (cudaStream_t)stream);
+}
+
 int dyn_net_dynamic(dyn_net_t net, const float* pts, const float* rgb_feat, const float* ray_dir,
                     const float* mask, float time, int R, int S, int V, float* raw, void* workspace,
                     size_t workspace_bytes, int precision, void* stream) {

@@ -195,12 +195,11 @@ __global__ void rgb_to_rgba_kernel(const float* __restrict__ in, float4* __restr
 }
 
 // Stand-alone projection + gather (Projector.compute_with_motions).
-// A 256-thread block owns 32 consecutive (point, view) pairs = 32 x 35 floats of
-// contiguous rgb_feat output.  8 lanes cooperate on one pair: lane 0 of the octet
-// does the projection / masks / view-angle math once and broadcasts the sampling
-// position with shuffles; lane j gathers feature channels 4j..4j+3 (float4 taps
-// from the channels-last map) and lanes 0..2 one RGB channel each.  Results are
-// staged in shared memory and written with coalesced 16-byte stores.
+// A 256-thread block owns 256 consecutive (point, view) pairs = 256 x 35 floats of
+// contiguous rgb_feat output: one projection per thread, then 8 lanes per pair for the
+// taps (lane j gathers feature channels 4j..4j+3 with float4 loads from the channels-last
+// map, lanes 0..2 one RGB channel each); results are staged in shared memory and written
+// with coalesced 16-byte stores.
 // Bilinear, zero padding, align_corners=True, coordinates normalised by the
 // SOURCE IMAGE size for both maps (projection.py:22-30, :143-158).
 __global__ void __launch_bounds__(256)
@@ -209,104 +208,115 @@ project_gather_kernel(const float* __restrict__ xyz_st, const float* __restrict_
                       const __grid_constant__ ViewCams cams, int V, long long N /* R*S */, int H,
                       int W, int h, int w, float* __restrict__ rgb_feat,
                       float* __restrict__ ray_diff, float* __restrict__ mask) {
-  __shared__ __align__(16) float stage[32 * kF];
-  const long long pair0 = (long long)blockIdx.x * 32;
-  const int lp = threadIdx.x >> 3;        // local pair
-  const int lane8 = threadIdx.x & 7;
-  const long long gid = pair0 + lp;
+  // A block owns 256 consecutive (point, view) pairs.  Phase 1: every thread projects ONE pair (all lanes
+  // busy; coalesced mask / ray_diff stores) and leaves the sampling position in shared memory.  Phase 2:
+  // eight rounds of 32 pairs, eight lanes per pair (four channels each from the channels-last map, lanes
+  // 0..2 one RGB channel), staged and written with coalesced 16-byte stores.
+  __shared__ __align__(16) float stage[2][32 * kF];
+  __shared__ float s_gx[256], s_gy[256];
+  __shared__ int s_v[256];
+  const long long pair0 = (long long)blockIdx.x * 256;
   const long long total = N * V;
-  const bool ok = gid < total;
-  float gx = 0.f, gy = 0.f;
-  int v = 0;
-  // (point, view) of this pair without a per-thread 64-bit division: one uniform
-  // division per block, then small 32-bit arithmetic
-  const long long q0 = pair0 / V;
-  const int t0 = (int)(pair0 - q0 * V) + lp;
-  if (lane8 == 0 && ok) {
-    const long long pt = q0 + t0 / V;
-    v = t0 % V;
-    const float sx = xyz_st[pt * 3], sy = xyz_st[pt * 3 + 1], sz = xyz_st[pt * 3 + 2];
-    float x = sx, y = sy, z = sz;
-    if (xyz != nullptr) {
-      const float* q = xyz + ((long long)v * N + pt) * 3;
-      x = q[0]; y = q[1]; z = q[2];
+  {
+    const long long gid = pair0 + threadIdx.x;
+    // (point, view) without a per-thread 64-bit division: one uniform division per block
+    const long long q0 = pair0 / V;
+    const int t0 = (int)(pair0 - q0 * V) + (int)threadIdx.x;
+    float gx = 0.f, gy = 0.f;
+    const int v = t0 % V;
+    if (gid < total) {
+      const long long pt = q0 + t0 / V;
+      const float sx = xyz_st[pt * 3], sy = xyz_st[pt * 3 + 1], sz = xyz_st[pt * 3 + 2];
+      float x = sx, y = sy, z = sz;
+      if (xyz != nullptr) {
+        const float* q = xyz + ((long long)v * N + pt) * 3;
+        x = q[0]; y = q[1]; z = q[2];
+      }
+      float u, vv;
+      bool front;
+      project_point(cams.P[v], x, y, z, u, vv, front);
+      gx = 2.f * u / (cams.w_img - 1.f) - 1.f;
+      gy = 2.f * vv / (cams.h_img - 1.f) - 1.f;
+      const bool inb = (u <= cams.w_img - 1.f) && (u >= 0.f) && (vv <= cams.h_img - 1.f) && (vv >= 0.f);
+      mask[gid] = (inb && front) ? 1.f : 0.f;
+      // compute_angle, projection.py:61-101
+      float a0 = cams.tgt[0] - sx, a1 = cams.tgt[1] - sy, a2 = cams.tgt[2] - sz;
+      normalize3(a0, a1, a2);
+      float b0 = cams.center[v][0] - x, b1 = cams.center[v][1] - y, b2 = cams.center[v][2] - z;
+      normalize3(b0, b1, b2);
+      float d0 = a0 - b0, d1 = a1 - b1, d2 = a2 - b2;
+      const float dot = a0 * b0 + a1 * b1 + a2 * b2;
+      normalize3(d0, d1, d2);
+      reinterpret_cast<float4*>(ray_diff)[gid] = make_float4(d0, d1, d2, dot);
     }
-    float u, vv;
-    bool front;
-    project_point(cams.P[v], x, y, z, u, vv, front);
-    gx = 2.f * u / (cams.w_img - 1.f) - 1.f;
-    gy = 2.f * vv / (cams.h_img - 1.f) - 1.f;
-    const bool inb = (u <= cams.w_img - 1.f) && (u >= 0.f) && (vv <= cams.h_img - 1.f) && (vv >= 0.f);
-    mask[gid] = (inb && front) ? 1.f : 0.f;
-    // compute_angle, projection.py:61-101
-    float a0 = cams.tgt[0] - sx, a1 = cams.tgt[1] - sy, a2 = cams.tgt[2] - sz;
-    normalize3(a0, a1, a2);
-    float b0 = cams.center[v][0] - x, b1 = cams.center[v][1] - y, b2 = cams.center[v][2] - z;
-    normalize3(b0, b1, b2);
-    float d0 = a0 - b0, d1 = a1 - b1, d2 = a2 - b2;
-    const float dot = a0 * b0 + a1 * b1 + a2 * b2;
-    normalize3(d0, d1, d2);
-    reinterpret_cast<float4*>(ray_diff)[gid] = make_float4(d0, d1, d2, dot);
-  }
-  // broadcast the sampling position inside the octet
-  const unsigned src = (threadIdx.x & 31) & ~7u;
-  gx = __shfl_sync(0xffffffffu, gx, src);
-  gy = __shfl_sync(0xffffffffu, gy, src);
-  v = __shfl_sync(0xffffffffu, v, src);
-  if (ok) {
-    {  // deep features, channels 4*lane8 .. +3
-      const float fx = (gx + 1.f) * 0.5f * (float)(w - 1);
-      const float fy = (gy + 1.f) * 0.5f * (float)(h - 1);
-      const float x0f = floorf(fx), y0f = floorf(fy);
-      const int x0 = (int)x0f, y0 = (int)y0f;
-      const float ax = fx - x0f, ay = fy - y0f;              // ATen grid_sampler weights:
-      const float bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;  // (ix_se - ix) etc.
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* base = feat_cl + (size_t)v * (size_t)(h * w * kC) + lane8 * 4;
-#pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int xi = x0 + dx, yi = y0 + dy;
-          const float wgt = (dx ? ax : bx) * (dy ? ay : by);
-          if (xi >= 0 && xi < w && yi >= 0 && yi < h) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(base + (yi * w + xi) * kC));
-            acc.x += t.x * wgt; acc.y += t.y * wgt; acc.z += t.z * wgt; acc.w += t.w * wgt;
-          }
-        }
-      float* o = stage + lp * kF + 3 + lane8 * 4;
-      o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
-    }
-    if (lane8 < 3) {  // RGB channel lane8 from [V,H,W,3]
-      const float fx = (gx + 1.f) * 0.5f * (float)(W - 1);
-      const float fy = (gy + 1.f) * 0.5f * (float)(H - 1);
-      const float x0f = floorf(fx), y0f = floorf(fy);
-      const int x0 = (int)x0f, y0 = (int)y0f;
-      const float ax = fx - x0f, ay = fy - y0f;
-      const float bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
-      float acc = 0.f;
-      const float* base = rgbs + (size_t)v * (size_t)(H * W * 3) + lane8;
-#pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int xi = x0 + dx, yi = y0 + dy;
-          const float wgt = (dx ? ax : bx) * (dy ? ay : by);
-          if (xi >= 0 && xi < W && yi >= 0 && yi < H)
-            acc += __ldg(base + (yi * W + xi) * 3) * wgt;
-        }
-      stage[lp * kF + lane8] = acc;
-    }
+    s_gx[threadIdx.x] = gx; s_gy[threadIdx.x] = gy; s_v[threadIdx.x] = v;
   }
   __syncthreads();
-  // 32 pairs x 35 floats = 1120 contiguous floats (pair0 * 35 floats is 16-byte aligned: 32*35*4 B per block)
-  const long long n_out = (total - pair0 < 32 ? total - pair0 : 32) * kF;
-  float* dst = rgb_feat + pair0 * kF;
-  for (int i = threadIdx.x * 4; i < n_out; i += 256 * 4) {
-    if (i + 4 <= n_out) {
-      *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(stage + i);
-    } else {
-      for (int j = i; j < n_out; ++j) dst[j] = stage[j];
+  const int lp = threadIdx.x >> 3;  // pair inside the round
+  const int lane8 = threadIdx.x & 7;
+#pragma unroll 1
+  for (int round = 0; round < 8; ++round) {
+    const long long base_pair = pair0 + round * 32;
+    if (base_pair >= total) break;
+    float* stg = stage[round & 1];
+    const int sp = round * 32 + lp;
+    if (base_pair + lp < total) {
+      const float gx = s_gx[sp], gy = s_gy[sp];
+      const int v = s_v[sp];
+      {  // deep features, channels 4*lane8 .. +3
+        const float fx = (gx + 1.f) * 0.5f * (float)(w - 1);
+        const float fy = (gy + 1.f) * 0.5f * (float)(h - 1);
+        const float x0f = floorf(fx), y0f = floorf(fy);
+        const int x0 = (int)x0f, y0 = (int)y0f;
+        const float ax = fx - x0f, ay = fy - y0f;                  // ATen grid_sampler weights:
+        const float bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;  // (ix_se - ix) etc.
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* base = feat_cl + (size_t)v * (size_t)(h * w * kC) + lane8 * 4;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int xi = x0 + dx, yi = y0 + dy;
+            const float wgt = (dx ? ax : bx) * (dy ? ay : by);
+            if (xi >= 0 && xi < w && yi >= 0 && yi < h) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(base + (yi * w + xi) * kC));
+              acc.x += t.x * wgt; acc.y += t.y * wgt; acc.z += t.z * wgt; acc.w += t.w * wgt;
+            }
+          }
+        float* o = stg + lp * kF + 3 + lane8 * 4;
+        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+      }
+      if (lane8 < 3) {  // RGB channel lane8 from [V,H,W,3]
+        const float fx = (gx + 1.f) * 0.5f * (float)(W - 1);
+        const float fy = (gy + 1.f) * 0.5f * (float)(H - 1);
+        const float x0f = floorf(fx), y0f = floorf(fy);
+        const int x0 = (int)x0f, y0 = (int)y0f;
+        const float ax = fx - x0f, ay = fy - y0f;
+        const float bx = (x0f + 1.f) - fx, by = (y0f + 1.f) - fy;
+        float acc = 0.f;
+        const float* base = rgbs + (size_t)v * (size_t)(H * W * 3) + lane8;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int xi = x0 + dx, yi = y0 + dy;
+            const float wgt = (dx ? ax : bx) * (dy ? ay : by);
+            if (xi >= 0 && xi < W && yi >= 0 && yi < H)
+              acc += __ldg(base + (yi * W + xi) * 3) * wgt;
+          }
+        stg[lp * kF + lane8] = acc;
+      }
+    }
+    __syncthreads();  // the two stage buffers alternate: the next round writes the other one
+    // 32 pairs x 35 floats = 1120 contiguous floats (base_pair * 35 floats is 16-byte aligned)
+    const long long n_out = (total - base_pair < 32 ? total - base_pair : 32) * kF;
+    float* dst = rgb_feat + base_pair * kF;
+    for (int i = threadIdx.x * 4; i < n_out; i += 256 * 4) {
+      if (i + 4 <= n_out) {
+        *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(stg + i);
+      } else {
+        for (int j = i; j < n_out; ++j) dst[j] = stg[j];
+      }
     }
   }
 }
@@ -675,7 +685,7 @@ int dyn_project_gather(const float* xyz_st, const float* xyz, const float* query
   DYN_LAUNCH_CHECK();
   long long N = (long long)R * S;
   ProfScope prof(PROF_GATHER, st);
-  project_gather_kernel<<<cdiv(N * V, 32), 256, 0, st>>>(xyz_st, xyz, src_rgbs, feat_cl_ws, vc,
+  project_gather_kernel<<<cdiv(N * V, 256), 256, 0, st>>>(xyz_st, xyz, src_rgbs, feat_cl_ws, vc,
                                                             V, N, H, W, h, w, rgb_feat, ray_diff,
                                                             mask);
   DYN_LAUNCH_CHECK();

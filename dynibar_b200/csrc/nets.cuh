@@ -38,5 +38,13 @@ bool attention_tc_supported(int S);
 int launch_attention_tc(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V,
                         const float* nvalid, long long P, int S, __nv_bfloat16* O, cudaStream_t st);
 int zero_last_samples(float* coeff, int R, int S, int width, cudaStream_t st);
+// training slice of the MotionMLP (motion_train.cu); embedding hooks live in nets_f32.cu
+int motion_embed(const float* xyzt, long long N, float* x0, cudaStream_t st);
+void motion_freqs(float f[16]);
+size_t motion_train_workspace(long long N);
+int motion_train_forward(const dyn_net* n, const float* xyzt, long long N, float* coeff, void* ws,
+                         size_t ws_bytes, cudaStream_t st);
+int motion_train_backward(const dyn_net* n, const float* xyzt, const float* d_coeff, long long N, void* ws,
+                          size_t ws_bytes, float* d_params, float* d_xyzt, cudaStream_t st);
 
 }  // namespace dyn

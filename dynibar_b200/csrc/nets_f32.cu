@@ -851,6 +851,15 @@ int motion_f32(const dyn_net* n, const float* x, int ldx, bool time_is_column, f
   return DYN_OK;
 }
 
+// hooks for the training slice (motion_train.cu): the embedding of xyzt [N,4] and its frequencies
+int motion_embed(const float* xyzt, long long N, float* x0, cudaStream_t st) {
+  return launch_pe(xyzt, 4, 4, 0, 0.f, 16, true, N, x0, st);
+}
+void motion_freqs(float f[16]) {
+  const PEFreqs q = pe_freqs(16, true);
+  for (int k = 0; k < 16; ++k) f[k] = q.f[k];
+}
+
 // ---------------------------------------------------------------------------
 // Fused (DYN_PREC_BF16) evaluation: per-view stage in ONE tcgen05 kernel
 // (nets_fused.cu: projection + gather + per-view MLP chain + pooling), then the

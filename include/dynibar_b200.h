@@ -252,6 +252,18 @@ int dyn_project_gather_backward(const float* xyz_st, const float* xyz, const flo
                                 int C, int h, int w, float* g_featmaps, float* g_xyz,
                                 void* stream);
 
+/* MotionMLP training slice (ibrnet/mlp_network.py:605-618; gradients as torch.autograd would produce them
+ * for MotionMLP.forward).  The forward keeps the embedding and the eight post-ReLU activations in `saved`
+ * (dyn_motion_train_workspace_bytes(N) bytes, also scratch for the backward).  The backward ACCUMULATES
+ * d(loss)/d(params) into d_params (flat, the n_params floats of dyn_net_create, same layout as the
+ * blob given to dyn_net_create; the caller zeroes it) and writes d(loss)/d(xyzt) [N,4] unless d_xyzt is NULL.
+ * fp32; split-K float atomics (not bit-reproducible between runs). */
+size_t dyn_motion_train_workspace_bytes(int N);
+int dyn_motion_mlp_train_forward(dyn_net_t motion, const float* xyzt, int N, float* coeff, void* saved,
+                                 size_t saved_bytes, void* stream);
+int dyn_motion_mlp_backward(dyn_net_t motion, const float* xyzt, const float* d_coeff, int N, void* saved,
+                            size_t saved_bytes, float* d_params, float* d_xyzt, void* stream);
+
 /* ---- f1: 2-D feature encoder, ResNet.forward as the reference runs it (feature_network.py:302-311) ----
  * conv 7x7 stride 2 (reflect) -> InstanceNorm -> ReLU -> layer1 (3 BasicBlocks, the first with stride 2)
  * -> 1x1 conv -> coarse (channels 0..31) | fine (channels 32..63).  images [N,3,H,W] fp32;

@@ -63,3 +63,41 @@ def test_project_gather_backward_matches_oracle_autograd(golden, name):
   gx, wx = sd.grad.cpu()[inb], so.grad[inb]
   bad = ((gx - wx).abs() > 1e-3 + 1e-3 * wx.abs()).float().mean().item()
   assert bad < 2e-3, bad
+
+
+@pytest.mark.parametrize("N,nb,tol", [(300, 6, 1e-3), (5000, 4, 1e-2)])
+def test_motion_mlp_backward_matches_oracle_autograd(N, nb, tol):
+  """MotionMLP (mlp_network.py:605-618): coefficients, d/d(every parameter) and d/d(xyzt) against autograd through
+  the oracle's restatement (in float64); 5000 rows exercise the split-K accumulation of the weight gradients.
+  Bar: 1e-3 relative in the L2 norm per tensor (max-abs: 5x that of the largest entry) on 300 rows.  A
+  pre-activation within rounding distance of 0 can take the other side of the ReLU kink on the GPU (different
+  summation order); with random upstream gradients one row is ~1/sqrt(N) of a gradient's norm, so each such flip
+  moves a tensor by ~1e-3 relative.  The 5000-row case (about ten expected flips in 10 M activations) therefore
+  uses 1e-2: a wrong or missing split-K partial sum would be an O(1) error."""
+  from dynibar_b200 import autograd as ag, mlp_network as nets
+  torch.manual_seed(N)
+  mod = nets.MotionMLP(num_basis=nb)
+  with torch.no_grad():  # the shipped init zeroes coeff_linear (mlp_network.py:602-603)
+    mod.coeff_linear.weight.normal_(0, 0.05)
+    mod.coeff_linear.bias.normal_(0, 0.05)
+  xyzt = torch.cat([torch.randn(N, 3) * 2, torch.rand(N, 1)], -1)
+  gen = torch.randn(N, 3 * nb)
+  # ---- oracle + torch autograd (CPU, fp32) ----
+  w = {k: v.detach().clone().double().requires_grad_(True) for k, v in mod.state_dict().items()}
+  xo = xyzt.clone().double().requires_grad_(True)
+  want = orc.motion_mlp(w, xo)
+  (want * gen.double()).sum().backward()
+  want = want.float()
+  # ---- library ----
+  mod = mod.to(DEV)
+  xd = xyzt.to(DEV).requires_grad_(True)
+  got = ag.motion_mlp(mod, xd)
+  torch.testing.assert_close(got.detach().cpu(), want.detach(), rtol=1e-4, atol=1e-5)
+  (got * gen.to(DEV)).sum().backward()
+  def close(name, got_t, ref):
+    d = got_t.detach().cpu().double() - ref
+    assert d.norm().item() <= tol * ref.norm().item() + 1e-12, (name, d.norm().item(), ref.norm().item())
+    assert d.abs().max().item() <= 5 * tol * ref.abs().max().item() + 1e-12, (name, d.abs().max().item())
+  for k, p in mod.named_parameters():
+    close(k, p.grad, w[k].grad)
+  close("xyzt", xd.grad, xo.grad)
