@@ -54,6 +54,9 @@ def parse():
   ap.add_argument("--cpu-rays", type=int, default=512, help="rays per timed chunk of the in-line cpu_baseline")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-extras", action="store_true", help="skip the kernel-timing pass, the 7+11-view line and weak_scaling")
+  ap.add_argument("--chunk", type=int, default=WORKLOAD["chunk"],
+                  help="rays per render_rays_mv call (the reference's chunk_size knob: 'decrease if running out "
+                       "of memory', config.py:168; results do not depend on it)")
   ap.add_argument("--view-kernel", default="default", choices=["default", "twin", "quad", "pipe"],
                   help="per-view stage kernel: library default, twin-warp, quad schedule, or sub-round pipelined twin")
   return ap.parse_args()
@@ -176,10 +179,10 @@ def main():
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
-  w = WORKLOAD
+  w = dict(WORKLOAD, chunk=a.chunk)
   config = {"workload": "BASELINE configs[1] shape: synthetic 512x288 frame, 64 coarse + 64 fine "
                         "samples (fine pass evaluates 128), 8 dynamic + 8 static source views, "
-                        "render_rays_mv, det=True, inv_uniform=True, chunk 8192",
+                        "render_rays_mv, det=True, inv_uniform=True, chunk %d" % a.chunk,
             "rays_per_frame": a.rays, "precision": a.precision,
             "l2": "per-step working set (source maps 66 MB + GBs of per-chunk intermediates) exceeds the "
                   "126 MB L2; plus an explicit 256 MB flush between steps"}

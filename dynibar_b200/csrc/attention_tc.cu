@@ -424,19 +424,21 @@ int launch_attention_tc(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __
   const int smem = kSmemAttn;
   ProfScope prof(PROF_ATTENTION, st);
   static const bool generic = getenv("DYN_ATTENTION") && !strcmp(getenv("DYN_ATTENTION"), "generic");
-  if ((S == 64 || S == 128) && !generic) {
-    if (S == 64) {
-      DYN_CUDA(cudaFuncSetAttribute(attention_twin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attention_twin_kernel<1><<<grid, 256, smem, st>>>(Q, K, V, nvalid, P, O);
-    } else {
-      DYN_CUDA(cudaFuncSetAttribute(attention_twin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attention_twin_kernel<2><<<grid, 256, smem, st>>>(Q, K, V, nvalid, P, O);
-    }
-  } else if (S % 64 == 0) {  // twin warps
+  static bool attr_done = false;  // one device per process (torch.distributed: one rank per GPU)
+  if (!attr_done) {
+    DYN_CUDA(cudaFuncSetAttribute(attention_twin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DYN_CUDA(cudaFuncSetAttribute(attention_twin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     DYN_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DYN_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  if (S == 64 && !generic) {
+    attention_twin_kernel<1><<<grid, 256, smem, st>>>(Q, K, V, nvalid, P, O);
+  } else if (S == 128 && !generic) {
+    attention_twin_kernel<2><<<grid, 256, smem, st>>>(Q, K, V, nvalid, P, O);
+  } else if (S % 64 == 0) {  // twin warps
     attention_tc_kernel<true><<<grid, 256, smem, st>>>(Q, K, V, nvalid, P, S, O);
   } else {
-    DYN_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attention_tc_kernel<false><<<grid, 128, smem, st>>>(Q, K, V, nvalid, P, S, O);
   }
   DYN_LAUNCH_CHECK();
