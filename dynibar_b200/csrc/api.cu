@@ -329,4 +329,54 @@ int dyn_net_static(dyn_net_t net, const float* pts, const float* ref_rays, const
                         workspace_bytes, precision, (cudaStream_t)stream);
 }
 
+size_t dyn_net_train_workspace_bytes(int kind, int R, int S, int V) {
+  if (kind != DYN_NET_DYNAMIC && kind != DYN_NET_STATIC) return 0;
+  return net_train_workspace(kind, R, S, V);
+}
+
+size_t dyn_net_backward_scratch_bytes(int kind, int R, int S, int V) {
+  if (kind != DYN_NET_DYNAMIC && kind != DYN_NET_STATIC) return 0;
+  return net_backward_scratch(kind, R, S, V);
+}
+
+int dyn_net_dynamic_train_forward(dyn_net_t net, const float* pts, const float* rgb_feat, const float* ray_dir,
+                                  const float* mask, float time, int R, int S, int V, float* raw, void* saved,
+                                  size_t saved_bytes, void* stream) {
+  if (R == 0) return DYN_OK;
+  DYN_CHECK_ARG(net && net->kind == DYN_NET_DYNAMIC && pts && rgb_feat && ray_dir && mask && raw && saved);
+  DYN_CHECK_ARG(R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
+  return net_dynamic_f32(net, pts, rgb_feat, ray_dir, mask, time, R, S, V, raw, saved, saved_bytes, DYN_PREC_FP32,
+                         (cudaStream_t)stream, /*train=*/true);
+}
+
+int dyn_net_dynamic_backward(dyn_net_t net, const float* pts, const float* mask, int R, int S, int V,
+                             const float* d_raw, void* saved, size_t saved_bytes, void* scratch,
+                             size_t scratch_bytes, float* d_params, float* d_rgb_feat, float* d_pts, void* stream) {
+  if (R == 0) return DYN_OK;
+  DYN_CHECK_ARG(net && net->kind == DYN_NET_DYNAMIC && pts && mask && d_raw && saved && scratch && d_params);
+  DYN_CHECK_ARG(R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
+  return net_dynamic_backward(net, pts, nullptr, nullptr, mask, R, S, V, d_raw, saved, saved_bytes, scratch,
+                              scratch_bytes, d_params, d_rgb_feat, d_pts, (cudaStream_t)stream);
+}
+
+int dyn_net_static_train_forward(dyn_net_t net, const float* pts, const float* ref_rays, const float* src_rays,
+                                 const float* rgb_feat, const float* ray_diff, const float* mask, int R, int S,
+                                 int V, float* raw, void* saved, size_t saved_bytes, void* stream) {
+  if (R == 0) return DYN_OK;
+  DYN_CHECK_ARG(net && net->kind == DYN_NET_STATIC && pts && ref_rays && src_rays && rgb_feat);
+  DYN_CHECK_ARG(ray_diff && mask && raw && saved && R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
+  return net_static_f32(net, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask, R, S, V, raw, saved, saved_bytes,
+                        DYN_PREC_FP32, (cudaStream_t)stream, /*train=*/true);
+}
+
+int dyn_net_static_backward(dyn_net_t net, const float* rgb_feat, const float* ray_diff, int R, int S, int V,
+                            const float* d_raw, void* saved, size_t saved_bytes, void* scratch,
+                            size_t scratch_bytes, float* d_params, float* d_rgb_feat, void* stream) {
+  if (R == 0) return DYN_OK;
+  DYN_CHECK_ARG(net && net->kind == DYN_NET_STATIC && rgb_feat && ray_diff && d_raw && saved && scratch && d_params);
+  DYN_CHECK_ARG(R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
+  return net_static_backward(net, rgb_feat, ray_diff, R, S, V, d_raw, saved, saved_bytes, scratch, scratch_bytes,
+                             d_params, d_rgb_feat, (cudaStream_t)stream);
+}
+
 }  // extern "C"

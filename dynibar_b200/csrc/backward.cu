@@ -44,20 +44,24 @@ __device__ __forceinline__ float warp_scan_mul_b(float v, int lane) {
 constexpr int kMaxSeg = 8;  // S <= 256
 
 // g_rays [R,11]: d/d(rgb 3, rgb_static 3, rgb_dy 3, depth, mask(ignored)); g_samples [5,R,S]:
-// d/d(alpha_dy, weights_dy, weights_st, alpha, weights) or null
+// d/d(alpha_dy, weights_dy, weights_st, alpha, weights) or null.
+// vanilla (raw2outputs_vanilla, render_ray.py:134-211 == the same compositing with no second net: raw_b = null):
+// g_rays [R,5] = d/d(rgb 3, depth, mask(ignored)), g_samples [2,R,S] = d/d(weights, alpha) or null.
 __global__ void composite_backward_kernel(const float* __restrict__ raw_a, const float* __restrict__ raw_b,
                                           const float* __restrict__ z_vals, const float* __restrict__ g_rays,
                                           const float* __restrict__ g_samples, int R, int S,
-                                          float* __restrict__ g_raw_a, float* __restrict__ g_raw_b) {
+                                          float* __restrict__ g_raw_a, float* __restrict__ g_raw_b, int vanilla) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
   const long long RS = (long long)R * S;
   const int nseg = (S + 31) / 32;
-  const float* gr = g_rays + (long long)r * 11;
-  const float gA[3] = {gr[0] + gr[6], gr[1] + gr[7], gr[2] + gr[8]};  // d/d c_dy weights: rgb + rgb_dy
-  const float gB[3] = {gr[0] + gr[3], gr[1] + gr[4], gr[2] + gr[5]};  // rgb + rgb_static
-  const float gdepth = gr[9];
+  const float* gr = g_rays + (long long)r * (vanilla ? 5 : 11);
+  const float gA[3] = {vanilla ? gr[0] : gr[0] + gr[6], vanilla ? gr[1] : gr[1] + gr[7],
+                       vanilla ? gr[2] : gr[2] + gr[8]};  // d/d c_dy weights: rgb + rgb_dy
+  const float gB[3] = {vanilla ? 0.f : gr[0] + gr[3], vanilla ? 0.f : gr[1] + gr[4],
+                       vanilla ? 0.f : gr[2] + gr[5]};    // rgb + rgb_static
+  const float gdepth = vanilla ? gr[3] : gr[9];
   // forward quantities per (segment, lane)
   float aA[kMaxSeg], aB[kMaxSeg], T[kMaxSeg], G[kMaxSeg];
   float carry = 1.f;
@@ -65,10 +69,10 @@ __global__ void composite_backward_kernel(const float* __restrict__ raw_a, const
     const int s = sg * 32 + lane;
     const bool ok = s < S;
     const long long p = (long long)r * S + (ok ? s : 0);
-    const float sa = ok ? raw_a[p * 4 + 3] : 0.f, sb = ok ? raw_b[p * 4 + 3] : 0.f;
+    const float sa = ok ? raw_a[p * 4 + 3] : 0.f, sb = (ok && !vanilla) ? raw_b[p * 4 + 3] : 0.f;
     const float delta = (s == S - 1) ? 1e10f : 1.f;
     aA[sg] = ok ? 1.f - expf(-softplus_f(sa) * delta) : 0.f;
-    aB[sg] = ok ? 1.f - expf(-softplus_f(sb) * delta) : 0.f;
+    aB[sg] = (ok && !vanilla) ? 1.f - expf(-softplus_f(sb) * delta) : 0.f;
     const float al = 1.f - (1.f - aB[sg]) * (1.f - aA[sg]);
     const float f = ok ? (1.f - al + 1e-10f) : 1.f;
     const float inc = warp_scan_mul_b(f, lane);
@@ -86,14 +90,15 @@ __global__ void composite_backward_kernel(const float* __restrict__ raw_a, const
     float z = 0.f;
     if (ok) {
       ca = reinterpret_cast<const float4*>(raw_a)[p];
-      cb = reinterpret_cast<const float4*>(raw_b)[p];
+      if (!vanilla) cb = reinterpret_cast<const float4*>(raw_b)[p];
       z = z_vals[p];
     }
-    const float gs_aA = (ok && g_samples) ? g_samples[0 * RS + p] : 0.f;
-    const float gs_wA = (ok && g_samples) ? g_samples[1 * RS + p] : 0.f;
-    const float gs_wB = (ok && g_samples) ? g_samples[2 * RS + p] : 0.f;
-    const float gs_al = (ok && g_samples) ? g_samples[3 * RS + p] : 0.f;
-    const float gs_w = (ok && g_samples) ? g_samples[4 * RS + p] : 0.f;
+    const bool gs_ok = ok && g_samples != nullptr;
+    const float gs_aA = (gs_ok && !vanilla) ? g_samples[0 * RS + p] : 0.f;
+    const float gs_wA = (gs_ok && !vanilla) ? g_samples[1 * RS + p] : 0.f;
+    const float gs_wB = (gs_ok && !vanilla) ? g_samples[2 * RS + p] : 0.f;
+    const float gs_al = gs_ok ? g_samples[(vanilla ? 1 : 3) * RS + p] : 0.f;
+    const float gs_w = gs_ok ? g_samples[(vanilla ? 0 : 4) * RS + p] : 0.f;
     const float al = 1.f - (1.f - aB[sg]) * (1.f - aA[sg]);
     const float dwA = gs_wA + gA[0] * ca.x + gA[1] * ca.y + gA[2] * ca.z;   // dL/d w_dy
     const float dwB = gs_wB + gB[0] * cb.x + gB[1] * cb.y + gB[2] * cb.z;   // dL/d w_st
@@ -114,7 +119,7 @@ __global__ void composite_backward_kernel(const float* __restrict__ raw_a, const
       const float dsb = eb > 0.f ? daB * eb * delta * sigmoid_f(cb.w) : 0.f;
       const float wA = aA[sg] * T[sg], wB = aB[sg] * T[sg];
       reinterpret_cast<float4*>(g_raw_a)[p] = make_float4(gA[0] * wA, gA[1] * wA, gA[2] * wA, dsa);
-      reinterpret_cast<float4*>(g_raw_b)[p] = make_float4(gB[0] * wB, gB[1] * wB, gB[2] * wB, dsb);
+      if (!vanilla) reinterpret_cast<float4*>(g_raw_b)[p] = make_float4(gB[0] * wB, gB[1] * wB, gB[2] * wB, dsb);
     }
   }
 }
@@ -193,6 +198,41 @@ __global__ void gather_backward_kernel(const float* __restrict__ xyz, const floa
   }
 }
 
+// Trajectory combination (compute_traj_pts + the displacements built from it, render_ray.py:361-369, :462-500,
+// :1101-1176): out[i, p, a] = (base ? base[p, a] : 0) + sum_k coeff[p, a nb + k] D[i, k], where a row of D is a
+// difference of two rows of the DCT trajectory basis.  Linear in coeff and base.
+__global__ void traj_combine_kernel(const float* __restrict__ coeff, const float* __restrict__ D,
+                                    const float* __restrict__ base, int n, int nb, long long P,
+                                    float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * P * 3) return;
+  const int a = (int)(idx % 3);
+  const long long t = idx / 3;
+  const long long p = t % P;
+  const int i = (int)(t / P);
+  float s = base != nullptr ? base[p * 3 + a] : 0.f;
+  for (int k = 0; k < nb; ++k) s = fmaf(coeff[p * 3 * nb + a * nb + k], D[i * nb + k], s);
+  out[idx] = s;
+}
+
+__global__ void traj_combine_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ D, int n, int nb,
+                                        long long P, float* __restrict__ g_coeff, float* __restrict__ g_base) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * 3) return;
+  const long long p = idx / 3;
+  const int a = (int)(idx - p * 3);
+  float gb = 0.f;
+  float gc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = 0; i < n; ++i) {
+    const float g = g_out[((long long)i * P + p) * 3 + a];
+    gb += g;
+    for (int k = 0; k < nb; ++k) gc[k] = fmaf(g, D[i * nb + k], gc[k]);
+  }
+  if (g_base != nullptr) g_base[idx] = gb;
+  if (g_coeff != nullptr)
+    for (int k = 0; k < nb; ++k) g_coeff[p * 3 * nb + a * nb + k] = gc[k];
+}
+
 }  // namespace
 }  // namespace dyn
 
@@ -206,7 +246,18 @@ int dyn_composite_backward(const float* raw_dy, const float* raw_st, const float
   DYN_CHECK_ARG(raw_dy && raw_st && z_vals && g_rays && g_raw_dy && g_raw_st && S >= 1);
   if (S > 32 * kMaxSeg) return fail(DYN_E_INVALID, "composite backward supports S <= %d (got %d)", 32 * kMaxSeg, S);
   composite_backward_kernel<<<cdiv((long long)R * 32, 128), 128, 0, (cudaStream_t)stream>>>(
-      raw_dy, raw_st, z_vals, g_rays, g_samples, R, S, g_raw_dy, g_raw_st);
+      raw_dy, raw_st, z_vals, g_rays, g_samples, R, S, g_raw_dy, g_raw_st, 0);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
+int dyn_composite_vanilla_backward(const float* raw, const float* z_vals, const float* g_rays, const float* g_samples,
+                                   int R, int S, float* g_raw, void* stream) {
+  if (R == 0) return DYN_OK;
+  DYN_CHECK_ARG(raw && z_vals && g_rays && g_raw && S >= 1);
+  if (S > 32 * kMaxSeg) return fail(DYN_E_INVALID, "composite backward supports S <= %d (got %d)", 32 * kMaxSeg, S);
+  composite_backward_kernel<<<cdiv((long long)R * 32, 128), 128, 0, (cudaStream_t)stream>>>(
+      raw, nullptr, z_vals, g_rays, g_samples, R, S, g_raw, nullptr, 1);
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }
@@ -224,6 +275,25 @@ int dyn_project_gather_backward(const float* xyz_st, const float* xyz, const flo
   if (g_featmaps) DYN_CUDA(cudaMemsetAsync(g_featmaps, 0, (size_t)V * C * h * w * sizeof(float), st));
   gather_backward_kernel<<<cdiv(N * V, 256), 256, 0, st>>>(xyz, xyz_st, featmaps, src_rgbs, g_rgb_feat, vc, V, N, H, W,
                                                            C, h, w, g_featmaps, g_xyz);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
+int dyn_traj_combine(const float* coeff, const float* D, const float* base, int n, int nb, int P, float* out,
+                     void* stream) {
+  if (P == 0 || n == 0) return DYN_OK;
+  DYN_CHECK_ARG(coeff && D && out && n >= 1 && nb >= 1 && nb <= 8 && P >= 0);
+  traj_combine_kernel<<<cdiv((long long)n * P * 3, 256), 256, 0, (cudaStream_t)stream>>>(coeff, D, base, n, nb, P, out);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
+int dyn_traj_combine_backward(const float* g_out, const float* D, int n, int nb, int P, float* g_coeff, float* g_base,
+                              void* stream) {
+  if (P == 0) return DYN_OK;
+  DYN_CHECK_ARG(g_out && D && n >= 1 && nb >= 1 && nb <= 8 && P >= 0 && (g_coeff || g_base));
+  traj_combine_bwd_kernel<<<cdiv((long long)P * 3, 256), 256, 0, (cudaStream_t)stream>>>(g_out, D, n, nb, P, g_coeff,
+                                                                                       g_base);
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }

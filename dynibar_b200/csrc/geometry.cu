@@ -437,6 +437,56 @@ __global__ void flow_sf_kernel(const float* __restrict__ weights, const float* _
   }
 }
 
+// Backward of compute_optical_flow (render_ray.py:333-358): flows[v, r] = proj_v(sum_s w[r, s] pts_seq[v, r, s]) - uv
+// -> g_weights [R,S] and g_pts_seq [n_flow,R,S,3].  One warp per ray, S <= 256.
+__global__ void flow_backward_kernel(const float* __restrict__ weights, const float* __restrict__ pts_seq,
+                                     const float* __restrict__ g_flows, const __grid_constant__ FlowCams fc,
+                                     int n_flow, int R, int S, float* __restrict__ g_weights,
+                                     float* __restrict__ g_pts) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const long long N = (long long)R * S;
+  float gw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int v = 0; v < n_flow; ++v) {
+    float e[3] = {0.f, 0.f, 0.f};
+    for (int s = lane; s < S; s += 32) {
+      const float wv = weights[(long long)r * S + s];
+      const float* p = pts_seq + ((long long)v * N + (long long)r * S + s) * 3;
+      e[0] += wv * p[0]; e[1] += wv * p[1]; e[2] += wv * p[2];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      for (int o = 16; o > 0; o >>= 1) e[a] += __shfl_xor_sync(0xffffffffu, e[a], o);
+    float c[3], q[3];
+    for (int i = 0; i < 3; ++i)
+      c[i] = fc.Rw[v][i * 3] * e[0] + fc.Rw[v][i * 3 + 1] * e[1] + fc.Rw[v][i * 3 + 2] * e[2] + fc.tw[v][i];
+    for (int i = 0; i < 3; ++i)
+      q[i] = fc.Kc[v][i * 3] * c[0] + fc.Kc[v][i * 3 + 1] * c[1] + fc.Kc[v][i * 3 + 2] * c[2];
+    const float g0 = g_flows[((long long)v * R + r) * 2], g1 = g_flows[((long long)v * R + r) * 2 + 1];
+    const float gq[3] = {g0 / q[2], g1 / q[2], -(g0 * q[0] + g1 * q[1]) / (q[2] * q[2])};
+    float gc[3], ge[3];
+    for (int j = 0; j < 3; ++j) gc[j] = fc.Kc[v][j] * gq[0] + fc.Kc[v][3 + j] * gq[1] + fc.Kc[v][6 + j] * gq[2];
+    for (int j = 0; j < 3; ++j) ge[j] = fc.Rw[v][j] * gc[0] + fc.Rw[v][3 + j] * gc[1] + fc.Rw[v][6 + j] * gc[2];
+    int i = 0;
+    for (int s = lane; s < S; s += 32, ++i) {
+      const long long ps = (long long)r * S + s;
+      const float* p = pts_seq + ((long long)v * N + ps) * 3;
+      gw[i] += ge[0] * p[0] + ge[1] * p[1] + ge[2] * p[2];
+      if (g_pts != nullptr) {
+        const float wv = weights[ps];
+        float* o = g_pts + ((long long)v * N + ps) * 3;
+        o[0] = wv * ge[0]; o[1] = wv * ge[1]; o[2] = wv * ge[2];
+      }
+    }
+  }
+  if (g_weights != nullptr) {
+    int i = 0;
+    for (int s = lane; s < S; s += 32, ++i) g_weights[(long long)r * S + s] = gw[i];
+  }
+}
+
+
 // ---------------------------------------------------------------------------
 // host helpers
 // ---------------------------------------------------------------------------
@@ -793,6 +843,22 @@ int dyn_flow_sceneflow(const float* weights, const float* pts_seq, const float* 
   }
   flow_sf_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(weights, pts_seq, uv, coeff, fc,
                                                                n_flow, R, S, flows, exp_sf);
+  DYN_LAUNCH_CHECK();
+  return DYN_OK;
+}
+
+int dyn_flow_backward(const float* weights, const float* pts_seq, const float* src_cams, const float* g_flows,
+                      int n_flow, int R, int S, float* g_weights, float* g_pts_seq, void* stream) {
+  if (R == 0 || n_flow == 0) return DYN_OK;
+  DYN_CHECK_ARG(weights && pts_seq && src_cams && g_flows && (g_weights || g_pts_seq));
+  DYN_CHECK_ARG(n_flow >= 1 && n_flow <= kMaxViews && S >= 1 && S <= 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  static thread_local FlowCams fc;
+  memset(&fc, 0, sizeof(fc));
+  int rc = build_flow_cams(src_cams, n_flow, st, &fc);
+  if (rc) return rc;
+  flow_backward_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(weights, pts_seq, g_flows, fc, n_flow, R, S,
+                                                                     g_weights, g_pts_seq);
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }

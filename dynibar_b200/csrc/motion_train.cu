@@ -19,24 +19,13 @@
 #include "common.cuh"
 #include "linear_f32.cuh"
 #include "nets.cuh"
+#include "train_gemm.cuh"
 
 namespace dyn {
 
 namespace {
 
-// C[m, n] (+)= sum_k A(m, k) B(k, n);  A(m, k) = A[m * sam + k * sak], B(k, n) = B[k * sbk + n * sbn].
-// 64 x 64 x 16 tiles, 256 threads, 4 x 4 outputs per thread.  gridDim.z splits K; with more than one split
-// (or accumulate) the tile is added with atomicAdd.
-struct GemmArgs {
-  const float *A, *B;
-  float* C;
-  long long M, N, K;
-  long long sam, sak, sbk, sbn;
-  long long ldc;
-  int accumulate;
-  long long k_per_split;
-};
-
+// the product kernel behind launch_gemm (train_gemm.cuh): 64 x 64 x 16 tiles, 256 threads, 4 x 4 outputs per thread
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs a) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
@@ -60,7 +49,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs a) {
       {
         const int kk = b_nfast ? (idx >> 6) : (idx & 15), nn = b_nfast ? (idx & 63) : (idx >> 4);
         const long long n = n0 + nn, k = k0 + kk;
-        Bs[kk][nn] = (n < a.N && k < k_hi) ? a.B[k * a.sbk + n * a.sbn] : 0.f;
+        float bv = (n < a.N && k < k_hi) ? a.B[(a.bdiv > 1 ? k / a.bdiv : k) * a.sbk + n * a.sbn] : 0.f;
+        if (a.kscale != nullptr && k < k_hi) bv *= a.kscale[k];
+        Bs[kk][nn] = bv;
       }
     }
     __syncthreads();
@@ -90,6 +81,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs a) {
     }
 }
 
+}  // namespace
+
 int launch_gemm(GemmArgs a, bool split_k, cudaStream_t st) {
   if (a.M == 0 || a.N == 0) return DYN_OK;
   int splits = 1;
@@ -106,6 +99,8 @@ int launch_gemm(GemmArgs a, bool split_k, cudaStream_t st) {
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }
+
+namespace {
 
 // g[r, c] *= (out[r, c] > 0)   (ReLU backward; g has leading dimension ldg, out is dense [N, width])
 __global__ void relu_mask_kernel(float* __restrict__ g, long long ldg, const float* __restrict__ out, int width,
@@ -137,6 +132,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g
   }
 }
 
+}  // namespace
+
 int launch_colsum(const float* g, long long ldg, int width, long long N, float* db, cudaStream_t st) {
   if (N == 0) return DYN_OK;
   const long long rows_per_block = 2048;
@@ -145,6 +142,8 @@ int launch_colsum(const float* g, long long ldg, int width, long long N, float* 
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }
+
+namespace {
 
 // PeriodicEmbed backward (mlp_network.py:530-555, layout of pe_kernel in nets_f32.cu):
 // x0 = [x, cos(f_k x) (k = 0..n-1), sin(f_k x) (k = 0..n-1)], each block D = 4 wide

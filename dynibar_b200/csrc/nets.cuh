@@ -14,10 +14,10 @@ size_t net_static_f32_workspace(int R, int S, int V);
 size_t motion_f32_workspace(long long N);
 int net_dynamic_f32(const dyn_net* n, const float* pts, const float* rgb_feat, const float* ray_dir,
                     const float* mask, float time, int R, int S, int V, float* raw, void* ws,
-                    size_t ws_bytes, int prec, cudaStream_t st);
+                    size_t ws_bytes, int prec, cudaStream_t st, bool train = false);
 int net_static_f32(const dyn_net* n, const float* pts, const float* ref_rays, const float* src_rays,
                    const float* rgb_feat, const float* ray_diff, const float* mask, int R, int S, int V,
-                   float* raw, void* ws, size_t ws_bytes, int prec, cudaStream_t st);
+                   float* raw, void* ws, size_t ws_bytes, int prec, cudaStream_t st, bool train = false);
 int motion_f32(const dyn_net* n, const float* x, int ldx, bool time_is_column, float time, long long N,
                float* coeff, void* ws, size_t ws_bytes, int prec, cudaStream_t st);
 // fused DYN_PREC_BF16 path (per-view stage = nets_fused.cu)
@@ -46,5 +46,16 @@ int motion_train_forward(const dyn_net* n, const float* xyzt, long long N, float
                          size_t ws_bytes, cudaStream_t st);
 int motion_train_backward(const dyn_net* n, const float* xyzt, const float* d_coeff, long long N, void* ws,
                           size_t ws_bytes, float* d_params, float* d_xyzt, cudaStream_t st);
+
+// training backward of the two aggregation nets (nets_train.cu); the forward is net_*_f32(..., train = true)
+size_t net_train_workspace(int kind, int R, int S, int V);
+size_t net_backward_scratch(int kind, int R, int S, int V);
+int net_dynamic_backward(const dyn_net* n, const float* pts, const float* rgb_feat, const float* ray_dir,
+                         const float* mask, int R, int S, int V, const float* d_raw, void* ws, size_t ws_bytes,
+                         void* scratch, size_t scratch_bytes, float* d_params, float* d_rgb_feat, float* d_pts,
+                         cudaStream_t st);
+int net_static_backward(const dyn_net* n, const float* rgb_feat, const float* ray_diff, int R, int S, int V,
+                        const float* d_raw, void* ws, size_t ws_bytes, void* scratch, size_t scratch_bytes,
+                        float* d_params, float* d_rgb_feat, cudaStream_t st);
 
 }  // namespace dyn

@@ -8,6 +8,7 @@
 
 #include "linear_tc.cuh"
 #include "nets.cuh"
+#include "nets_f32_bufs.cuh"
 #include "nets_fused.cuh"
 #include "fused_engine.cuh"
 
@@ -244,13 +245,14 @@ __global__ void st_pool1_kernel(const float* __restrict__ rgb_feat, const float*
 }
 
 // x += x_res ; vis = sigmoid(x_vis[128]) * mask   (mlp_network.py:273-275)
-__global__ void vis1_kernel(float* __restrict__ x, const float* __restrict__ xvis,
-                            const float* __restrict__ mask, long long M, float* __restrict__ vis) {
+// (x2 may alias x: inference updates x in place, training keeps both)
+__global__ void vis1_kernel(const float* x, const float* __restrict__ xvis,
+                            const float* __restrict__ mask, long long M, float* x2, float* __restrict__ vis) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * 128) return;
   long long m = idx >> 7;
   int c = (int)(idx & 127);
-  x[idx] += xvis[m * 129 + c];
+  x2[idx] = x[idx] + xvis[m * 129 + c];
   if (c == 0) vis[m] = sigmoid_f(xvis[m * 129 + 128]) * mask[m];
 }
 
@@ -499,8 +501,9 @@ __global__ void st_out_kernel(const float* __restrict__ logit, const float* __re
 
 // time feature of the dynamic net: ray_dir_fc(PE(t)) -> 35 values, identical
 // for every (ray, sample, view) of a call (mlp_network.py:240-244). One block.
+// `keep` (training): dfeat[64..319] = hidden activations, dfeat[320..340] = PE(t)
 __global__ void dyn_time_feat_kernel(const float* __restrict__ prm, DynamicLayout L, float t,
-                                     float* __restrict__ dfeat) {
+                                     float* __restrict__ dfeat, int keep) {
   __shared__ float pe[21];
   __shared__ float h[256];
   int tid = threadIdx.x;
@@ -516,6 +519,10 @@ __global__ void dyn_time_feat_kernel(const float* __restrict__ prm, DynamicLayou
     float s = prm[L.ray_dir0.b + tid];
     for (int k = 0; k < 21; ++k) s = fmaf(prm[L.ray_dir0.w + tid * 21 + k], pe[k], s);
     h[tid] = elu_f(s);
+    if (keep) {
+      dfeat[64 + tid] = h[tid];
+      if (tid < 21) dfeat[320 + tid] = pe[tid];
+    }
   }
   __syncthreads();
   if (tid < kF) {
@@ -535,20 +542,6 @@ __global__ void zero_last_kernel(float* __restrict__ coeff, int R, int S, int n_
   long long r = t / n_last;
   coeff[(r * S + s) * width + c] *= 0.0f;  // reference multiplies by 0 (render_ray.py:472)
 }
-
-// ---------------------------------------------------------------------------
-// workspace bump allocator (also used to SIZE the workspace with base == null)
-// ---------------------------------------------------------------------------
-struct Bump {
-  char* base;
-  size_t off;
-  float* f(size_t n) {
-    off = (off + 255) & ~(size_t)255;
-    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
-    off += n * sizeof(float);
-    return p;
-  }
-};
 
 static const float* P_(const dyn_net* n, int off) { return off < 0 ? nullptr : n->params + off; }
 
@@ -573,21 +566,6 @@ int net_rows_per_chunk(int S, int V) {
   long long rows = 4194304;  // (point, view) rows per internal chunk (workspace ~1.5 KB/row)
   long long r = rows / ((long long)S * V);
   return (int)(r < 1 ? 1 : r);
-}
-
-// Shared trunk after the first pooling: base_fc ... ray transformer.
-// in_segs: the (mean,var | per-view feat) segments of base_fc's input.
-struct TrunkBufs {
-  float *H1, *X, *H2, *XV, *vis1, *vis2, *G, *nvalid, *GH, *G2, *Q, *K, *V, *O, *O2, *G3;
-};
-
-static void trunk_alloc(Bump& b, long long M, long long P, TrunkBufs* t) {
-  t->H1 = b.f(M * 256); t->X = b.f(M * 128); t->H2 = b.f(M * 128); t->XV = b.f(M * 129);
-  t->vis1 = b.f(M); t->vis2 = b.f(M); t->G = b.f(P * 257); t->nvalid = b.f(P);
-  // G2, Q, K, V, O double as the fused path's tile-layout buffers: whole 256-row iterations
-  const long long Pt = ((P + 255) / 256) * 256;
-  t->GH = b.f(P * 256); t->G2 = b.f(Pt * 128); t->Q = b.f(Pt * 128); t->K = b.f(Pt * 128);
-  t->V = b.f(Pt * 128); t->O = b.f(Pt * 128); t->O2 = b.f(P * 128); t->G3 = b.f(P * 128);
 }
 
 // per-point tail shared by the staged and the fused paths:
@@ -640,14 +618,14 @@ static int run_trunk(const dyn_net* n, const Layout& L, const Seg& mv, const Seg
   a.row_scale = weight1;
   RUN(run_lin(n, L.vis0, a, prec, st));
   RUN(run_lin(n, L.vis2, L1(n, L.vis2, t.H2, t.XV, M, ACT_ELU), prec, st));
-  vis1_kernel<<<cdiv(M * 128, 256), 256, 0, st>>>(t.X, t.XV, mask, M, t.vis1);
+  vis1_kernel<<<cdiv(M * 128, 256), 256, 0, st>>>(t.X, t.XV, mask, M, t.X2, t.vis1);
   DYN_LAUNCH_CHECK();
   // vis_fc2(x * vis) (:276 / :489)
-  a = L1(n, L.vis2_0, t.X, t.H2, M, ACT_ELU);
+  a = L1(n, L.vis2_0, t.X2, t.H3, M, ACT_ELU);
   a.row_scale = t.vis1;
   RUN(run_lin(n, L.vis2_0, a, prec, st));
-  RUN(run_lin(n, L.vis2_2, L1(n, L.vis2_2, t.H2, t.vis2, M, ACT_SIGMOID), prec, st));
-  pool2_kernel<<<cdiv(P * 128, 256), 256, 0, st>>>(t.X, t.vis2, mask, P, V, t.G, t.nvalid);
+  RUN(run_lin(n, L.vis2_2, L1(n, L.vis2_2, t.H3, t.vis2, M, ACT_SIGMOID), prec, st));
+  pool2_kernel<<<cdiv(P * 128, 256), 256, 0, st>>>(t.X2, t.vis2, mask, P, V, t.G, t.nvalid);
   DYN_LAUNCH_CHECK();
   mask_vis2_kernel<<<cdiv(M, 256), 256, 0, st>>>(t.vis2, mask, M);
   DYN_LAUNCH_CHECK();
@@ -657,22 +635,6 @@ static int run_trunk(const dyn_net* n, const Layout& L, const Seg& mv, const Seg
 // ---------------------------------------------------------------------------
 // DynibarDynamic.forward, fp32 (mlp_network.py:236-316)
 // ---------------------------------------------------------------------------
-struct DynBufs {
-  float *dfeat, *feat, *mv, *w1, *ptspe, *dirpe, *G4h, *G4, *sh, *sig, *ch, *ch2, *rgb;
-  TrunkBufs t;
-};
-
-static size_t dyn_alloc(Bump& b, int R, int S, int V, DynBufs* d) {
-  long long P = (long long)R * S, M = P * V;
-  d->dfeat = b.f(64);
-  d->feat = b.f(M * kF); d->mv = b.f(P * 2 * kF); d->w1 = b.f(M);
-  trunk_alloc(b, M, P, &d->t);
-  d->ptspe = b.f(P * 33); d->dirpe = b.f((long long)R * 27);
-  d->G4h = b.f(P * 256); d->G4 = b.f(P * 128); d->sh = b.f(P * 128); d->sig = b.f(P);
-  d->ch = b.f(P * 128); d->ch2 = b.f(P * 64); d->rgb = b.f(P * 3);
-  return b.off;
-}
-
 size_t net_dynamic_f32_workspace(int R, int S, int V) {
   Bump b{nullptr, 0};
   DynBufs d;
@@ -682,20 +644,21 @@ size_t net_dynamic_f32_workspace(int R, int S, int V) {
 
 int net_dynamic_f32(const dyn_net* n, const float* pts, const float* rgb_feat, const float* ray_dir,
                     const float* mask, float time, int R_all, int S, int V, float* raw, void* ws,
-                    size_t ws_bytes, int prec, cudaStream_t st) {
+                    size_t ws_bytes, int prec, cudaStream_t st, bool train) {
   const DynamicLayout& L = n->dl;
   const int RC = net_rows_per_chunk(S, V);
+  if (train && R_all > RC) return fail(DYN_E_INVALID, "training forward: %d rays exceed one internal chunk (%d)", R_all, RC);
   for (int r0 = 0; r0 < R_all; r0 += RC) {
     const int R = (R_all - r0) < RC ? (R_all - r0) : RC;
     const long long P = (long long)R * S, M = P * V, p0 = (long long)r0 * S;
     Bump b{(char*)ws, 0};
     DynBufs d;
-    if (dyn_alloc(b, R, S, V, &d) > ws_bytes)
+    if (dyn_alloc(b, R, S, V, &d, train) > ws_bytes)
       return fail(DYN_E_WORKSPACE, "net_dynamic: workspace %zu < %zu", ws_bytes, b.off);
     const float* c_pts = pts + p0 * 3;
     const float* c_feat = rgb_feat + p0 * V * kF;
     const float* c_mask = mask + p0 * V;
-    dyn_time_feat_kernel<<<1, 256, 0, st>>>(n->params, L, time, d.dfeat);
+    dyn_time_feat_kernel<<<1, 256, 0, st>>>(n->params, L, time, d.dfeat, train ? 1 : 0);
     DYN_LAUNCH_CHECK();
     dyn_pool1_kernel<<<cdiv(P * kF, 256), 256, 0, st>>>(c_feat, d.dfeat, c_mask, P, V, d.feat, d.mv, d.w1);
     DYN_LAUNCH_CHECK();
@@ -726,22 +689,6 @@ int net_dynamic_f32(const dyn_net* n, const float* pts, const float* rgb_feat, c
 // ---------------------------------------------------------------------------
 // DynibarStatic.forward, fp32 (mlp_network.py:423-527)
 // ---------------------------------------------------------------------------
-struct StBufs {
-  float *ptspe, *srcpe, *refpe, *H0, *SF, *reff, *feat70, *mv, *w1, *meff, *sh, *sig, *ch, *ch2, *logit;
-  TrunkBufs t;
-};
-
-static size_t st_alloc(Bump& b, int R, int S, int V, StBufs* d) {
-  long long P = (long long)R * S, M = P * V;
-  d->ptspe = b.f(P * 33); d->srcpe = b.f(M * 66); d->refpe = b.f((long long)R * 66);
-  d->H0 = b.f(M * 256); d->SF = b.f(M * kF); d->reff = b.f((long long)R * kF);
-  d->feat70 = b.f(M * 2 * kF); d->mv = b.f(P * 4 * kF); d->w1 = b.f(M); d->meff = b.f(M);
-  trunk_alloc(b, M, P, &d->t);
-  d->sh = b.f(P * 128); d->sig = b.f(P);
-  d->ch = b.f(M * 128); d->ch2 = b.f(M * 64); d->logit = b.f(M);
-  return b.off;
-}
-
 size_t net_static_f32_workspace(int R, int S, int V) {
   Bump b{nullptr, 0};
   StBufs d;
@@ -751,15 +698,16 @@ size_t net_static_f32_workspace(int R, int S, int V) {
 
 int net_static_f32(const dyn_net* n, const float* pts, const float* ref_rays, const float* src_rays,
                    const float* rgb_feat, const float* ray_diff, const float* mask, int R_all, int S,
-                   int V, float* raw, void* ws, size_t ws_bytes, int prec, cudaStream_t st) {
+                   int V, float* raw, void* ws, size_t ws_bytes, int prec, cudaStream_t st, bool train) {
   const StaticLayout& L = n->sl;
   const int RC = net_rows_per_chunk(S, V);
+  if (train && R_all > RC) return fail(DYN_E_INVALID, "training forward: %d rays exceed one internal chunk (%d)", R_all, RC);
   for (int r0 = 0; r0 < R_all; r0 += RC) {
     const int R = (R_all - r0) < RC ? (R_all - r0) : RC;
     const long long P = (long long)R * S, M = P * V, p0 = (long long)r0 * S;
     Bump b{(char*)ws, 0};
     StBufs d;
-    if (st_alloc(b, R, S, V, &d) > ws_bytes)
+    if (st_alloc(b, R, S, V, &d, train) > ws_bytes)
       return fail(DYN_E_WORKSPACE, "net_static: workspace %zu < %zu", ws_bytes, b.off);
     const float* c_feat = rgb_feat + p0 * V * kF;
     const float* c_rd = ray_diff + p0 * V * 4;
@@ -787,7 +735,7 @@ int net_static_f32(const dyn_net* n, const float* pts, const float* ref_rays, co
     RUN(run_lin(n, L.outgeo2, L1(n, L.outgeo2, d.sh, d.sig, P, ACT_NONE), prec, st));
     // rgb blending head on [g, x, vis, ray_diff] (:508-525)
     a = L1(n, L.rgb0, nullptr, d.ch, M, ACT_ELU);
-    a.seg[0] = Seg{d.t.G3, 128, 128, V}; a.seg[1] = Seg{d.t.X, 128, 128, 1};
+    a.seg[0] = Seg{d.t.G3, 128, 128, V}; a.seg[1] = Seg{d.t.X2, 128, 128, 1};
     a.seg[2] = Seg{d.t.vis2, 1, 1, 1}; a.seg[3] = Seg{c_rd, 4, 4, 1}; a.nseg = 4;
     RUN(run_lin(n, L.rgb0, a, prec, st));
     RUN(run_lin(n, L.rgb2, L1(n, L.rgb2, d.ch, d.ch2, M, ACT_ELU), prec, st));
@@ -875,7 +823,7 @@ static size_t fused_alloc(Bump& b, bool st_net, int R, int S, int V, FusedBufs* 
   const long long P = (long long)R * S, M = P * V;
   d->small = b.f(64);
   d->G = b.f(((P + 255) / 256) * 256 * (kGStride / 2));  // bf16 tile image, 34 k-groups, whole iterations
-  trunk_alloc(b, 0, P, &d->t);
+  trunk_alloc(b, 0, P, &d->t, false);
   d->sh = b.f(P * 128); d->sig = b.f(P);
   if (st_net) {
     d->refpl = b.f((long long)R * 6); d->refpe = b.f((long long)R * 66); d->reff = b.f((long long)R * kF);
@@ -1073,7 +1021,7 @@ int net_dynamic_fused(const dyn_net* n, const float* pts, const float* pts_seq, 
     FusedBufs d;
     if (fused_alloc(b, false, R, S, V, &d) > ws_bytes)
       return fail(DYN_E_WORKSPACE, "net_dynamic_fused: workspace %zu < %zu", ws_bytes, b.off);
-    dyn_time_feat_kernel<<<1, 256, 0, st>>>(n->params, L, time, d.small);
+    dyn_time_feat_kernel<<<1, 256, 0, st>>>(n->params, L, time, d.small, 0);
     DYN_LAUNCH_CHECK();
     va.pts = pts + p0 * 3; va.pts_seq = pts_seq + p0 * 3; va.seq_stride = P_all; va.P = P;
     va.ref_feat = nullptr; va.dfeat = d.small;

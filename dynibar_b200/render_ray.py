@@ -7,8 +7,12 @@ reference): `render_rays_mv` (render_ray.py:600), `render_rays_mono` (:870),
 `compute_src_plucker_coordinate` (:380), `z_to_s` (:399).
 
 All math runs in `csrc/` kernels through the C ABI (include/dynibar_b200.h);
-this file only allocates tensors and sequences calls.  Inference only: the
-kernels have no backward yet, so `requires_grad` inputs raise.
+this file only allocates tensors and sequences calls.  `render_rays_mono` is
+differentiable (training): when gradients are enabled and the
+model's parameters or the feature maps require grad it runs the fp32 training
+path (`_render_mono_train`, autograd Functions of dynibar_b200/autograd.py over
+the backward kernels).  `render_rays_mv` is the evaluation path (the reference
+calls it under no_grad) and refuses inputs that require grad.
 """
 
 from collections import OrderedDict
@@ -69,19 +73,23 @@ def _no_grad_only(*tensors):
         "call under torch.no_grad() with detached inputs")
 
 
-def _refuse_training(model, *featmaps):
-  """The orchestrators run under no_grad (forward-only kernels): a training loop that swapped the
-  import would get detached outputs and fail late (or silently).  Fail loudly instead."""
+def _wants_grad(model, *featmaps):
+  """True when gradients are enabled and a parameter of the model or a feature map requires grad."""
   if not torch.is_grad_enabled():
-    return
+    return False
   mods = [m for m in vars(model).values() if isinstance(m, torch.nn.Module)]
   live = any(p.requires_grad for m in mods for p in m.parameters())
-  live = live or any(torch.is_tensor(f) and f.requires_grad for fm in featmaps if fm is not None
+  return live or any(torch.is_tensor(f) and f.requires_grad for fm in featmaps if fm is not None
                      for f in fm if f is not None)
-  if live:
+
+
+def _refuse_training(model, *featmaps):
+  """render_rays_mv runs under no_grad (evaluation path; forward-only fused kernels): a training loop that
+  called it would get detached outputs and fail late (or silently).  Fail loudly instead."""
+  if _wants_grad(model, *featmaps):
     raise NotImplementedError(
-        "dynibar_b200 kernels are forward-only (training backward = SURVEY 8(f) f2): parameters or "
-        "feature maps require grad; call under torch.no_grad() or freeze them")
+        "dynibar_b200.render_rays_mv is the evaluation path (forward-only fused kernels): parameters or "
+        "feature maps require grad; call under torch.no_grad() or freeze them (training = render_rays_mono)")
 
 
 def _scalar(x):
@@ -592,9 +600,12 @@ def render_rays_mono(frame_idx, time_embedding, time_offset, ray_batch, model, f
                      N_samples, args, inv_uniform=False, N_importance=0, raw_noise_std=0.0,
                      det=False, white_bkgd=False, is_train=True, num_vv=2, jitter=None, precision=None):
   """Coarse-only rendering for monocular video (render_ray.py:870-1277), including the
-  cross-time branch (:1099-1270) when is_train=True.  Forward only: the kernels have no
-  backward yet, so everything runs under no_grad (training needs SURVEY 8(f) f2)."""
-  _refuse_training(model, featmaps)
+  cross-time branch (:1099-1270) when is_train=True.  With gradients enabled and parameters / feature
+  maps that require grad the differentiable fp32 training path runs (`_render_mono_train`); otherwise
+  the forward-only kernels (fused tcgen05 path in bf16 mode) under no_grad."""
+  if _wants_grad(model, featmaps):
+    return _render_mono_train(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, N_samples,
+                              args, inv_uniform, det, is_train, num_vv, jitter)
   with torch.no_grad(), precision_scope(precision):
     t = _scalar(time_embedding[0].float())
     ray_batch, hb = _with_host_copies(ray_batch, model, ("trajectory_basis",))
@@ -657,3 +668,96 @@ def _cross_time(ray_batch, feat_anchor, pts, z, aux, ref_idx, anc_idx, t_anc, an
   out_a_dy["occ_weights"], out_a_dy["occ_weight_map"] = occlusion_weights(out_ref_dy["weights"],
                                                                          out_a_dy["weights"])
   return {"outputs_coarse_anchor": out_a, "outputs_coarse_anchor_dy": out_a_dy}
+
+
+# ---------------------------------------------------------------------------
+# f2: differentiable render_rays_mono (training step)
+# ---------------------------------------------------------------------------
+def _render_mono_train(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, N_samples, args,
+                       inv_uniform, det, is_train, num_vv, jitter):
+  """render_rays_mono (render_ray.py:870-1277) with autograd: the same sequence as the reference, every stage a
+  `torch.autograd.Function` over the fp32 forward/backward kernels (dynibar_b200/autograd.py).  Gradients reach
+  the parameters of motion_mlp / net_coarse_dy / net_coarse_st and the feature maps.  torch itself only
+  concatenates the time column, zeroes the last samples' coefficients, slices and detaches."""
+  from dynibar_b200 import autograd as ag
+  t = _scalar(time_embedding[0].float())
+  rb, hb = _with_host_copies(ray_batch, model, ("trajectory_basis",))
+  basis = hb["trajectory_basis"]  # host [T, nb]; rows indexed like the reference (negative indices wrap)
+  fidx = int(frame_idx[0])
+  ref_offsets = [int(o) for o in time_offset[0]]
+  with torch.no_grad():
+    pts, z, s = sample_along_camera_ray(rb["ray_o"], rb["ray_d"], rb["depth_range"], N_samples, inv_uniform, det,
+                                        jitter)
+    ref_plucker = compute_ref_plucker_coordinate(rb["ray_o"], rb["ray_d"])
+    src_plucker = compute_src_plucker_coordinate(pts, rb["static_src_cameras"])
+  ray_dir = ref_plucker[:, :3]
+  dev = dev_of(pts)
+  R, S = pts.shape[:2]
+  n_last = int(round(S * 0.1))
+  keep = torch.ones(1, S, 1, device=dev)
+  if n_last > 0:
+    keep[:, S - n_last:] = 0.0
+  zero = torch.zeros_like(basis[0])
+
+  def rows(pairs):  # D[i] = basis[a_i] - basis[b_i] (b = None: zero row), on the device
+    return torch.stack([basis[a] - basis[b] if a is not None else zero for a, b in pairs]).to(dev)
+
+  def coeffs(p, tt):  # model.motion_mlp(cat[p, t]) with the last samples zeroed (:957-958, :1126-1127)
+    xyzt = torch.cat([p, torch.full((R, S, 1), tt, device=dev)], dim=-1)
+    return ag.motion_mlp(model.motion_mlp, xyzt) * keep
+
+  coeff = coeffs(pts, t)
+  seq = ag.traj_combine(coeff, rows([(fidx + o, fidx) for o in ref_offsets] + [(None, None)] * num_vv), pts)
+  cam = rb["camera"]
+  f_dy, _, m_dy = ag.project_gather(pts, seq, cam, rb["src_rgbs"], rb["src_cameras"], featmaps[0])
+  f_st, rd_st, m_st = ag.project_gather(pts, None, cam, rb["static_src_rgbs"], rb["static_src_cameras"],
+                                        featmaps[2])
+  raw_dy = ag.net_dynamic(model.net_coarse_dy, pts, f_dy, ray_dir, m_dy, t)
+  raw_st = ag.net_static(model.net_coarse_st, pts, ref_plucker, src_plucker, f_st, rd_st, m_st)
+  out = ag.composite(raw_dy, raw_st, z, m_dy, m_st, 1, 1)
+  out_st = ag.composite_vanilla(raw_st, z, m_st, 1)
+  out_dy = ag.composite_vanilla(raw_dy, z, m_dy, 1)
+  out["render_flows"] = ag.optical_flow(out["weights"], seq[:6], rb["src_cameras"][:, :6], rb["uv_grid"])
+  out["s_vals"] = s
+  with torch.no_grad():  # :1086-1096, detached in the reference
+    _, out["exp_sf"] = _flow_sceneflow(out["weights"], seq, rb["src_cameras"], rb["uv_grid"], coeff, basis, fidx,
+                                       1, 1)
+  ret = {"outputs_coarse": None, "outputs_fine": None, "outputs_coarse_ref": out,
+         "outputs_coarse_ref_dy": out_dy, "outputs_coarse_st": out_st}
+  if not is_train:
+    return ret
+  # ---- cross-time rendering for temporal consistency (:1099-1270)
+  anc = int(frame_idx[1])
+  t_anc = _scalar(time_embedding[1].float())
+  anchor_offsets = [int(o) for o in time_offset[1]]
+  sf_seq = ag.traj_combine(coeff, rows([(fidx + o, fidx + o - 1) for o in (-2, -1, 0, 1, 2, 3)]))
+  pts_anchor = ag.traj_combine(coeff, rows([(anc, fidx)]), pts)[0]
+  coeff_a = coeffs(pts_anchor, t_anc)
+  seq_a = ag.traj_combine(coeff_a, rows([(anc + o, anc) for o in anchor_offsets] + [(None, None)] * num_vv),
+                          pts_anchor)
+  kept = [(i, anc + o - fidx) for i, o in enumerate(anchor_offsets) if -3 <= anc + o - fidx <= 3]
+  pts_traj_anchor = seq_a[[i for i, _ in kept]]
+  pts_traj_ref = ag.traj_combine(coeff, rows([(fidx + ro, fidx) for _, ro in kept]), pts)
+  f_a, _, m_a = ag.project_gather(pts, seq_a, cam, rb["anchor_src_rgbs"], rb["anchor_src_cameras"], featmaps[1])
+  raw_a = ag.net_dynamic(model.net_coarse_dy, pts_anchor, f_a, ray_dir, m_a, t_anc)
+  # anchor samples count when ANY view sees them (render_ray.py:1198-1200)
+  out_a = ag.composite(raw_a, raw_st, z, m_a, m_st, 0, 1)
+  out_a_dy = ag.composite_vanilla(raw_a, z, m_a, 0)
+  occ_mode = args.occ_weights_mode
+  if occ_mode == 0:
+    key = "weights_dy" if abs(fidx - anc) > 1 else "weights"
+  elif occ_mode == 1:
+    key = "weights_dy"
+  elif occ_mode == 2:
+    key = "weights"
+  else:
+    raise NotImplementedError
+  with torch.no_grad():  # detached in the reference (:1222, :1254)
+    out_a["occ_weights"], out_a["occ_weight_map"] = occlusion_weights(out[key], out_a[key])
+    out_a_dy["occ_weights"], out_a_dy["occ_weight_map"] = occlusion_weights(out_dy["weights"], out_a_dy["weights"])
+  out_a["pts_traj_ref"] = pts_traj_ref
+  out_a["pts_traj_anchor"] = pts_traj_anchor
+  out_a["sf_seq"] = sf_seq
+  ret["outputs_coarse_anchor"] = out_a
+  ret["outputs_coarse_anchor_dy"] = out_a_dy
+  return ret

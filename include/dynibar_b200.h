@@ -264,6 +264,48 @@ int dyn_motion_mlp_train_forward(dyn_net_t motion, const float* xyzt, int N, flo
 int dyn_motion_mlp_backward(dyn_net_t motion, const float* xyzt, const float* d_coeff, int N, void* saved,
                             size_t saved_bytes, float* d_params, float* d_xyzt, void* stream);
 
+/* ---- f2: training step of the two aggregation networks (DynibarDynamic.forward, ibrnet/mlp_network.py:236-316;
+ * DynibarStatic.forward, :423-527; gradients as torch.autograd produces them for those modules).
+ * The *_train_forward calls are the fp32 forwards of dyn_net_dynamic / dyn_net_static that keep every activation in
+ * `saved` (dyn_net_train_workspace_bytes bytes; R rays must fit one internal chunk: R*S*V <= 4 Mi rows).  The
+ * backward reads `saved`, uses `scratch` (dyn_net_backward_scratch_bytes), ACCUMULATES d(loss)/d(params) into
+ * d_params (flat, layout of the blob given to dyn_net_create; the caller zeroes it) and writes
+ * d_rgb_feat [R,S,V,35] (gradient w.r.t. the gathered colours + features; NULL to skip) and, for the dynamic net,
+ * d_pts [R,S,3] (through the positional encoding of ref_pts_fc; NULL to skip).  mask / ray_diff / rays / time carry
+ * no gradient (the reference detaches them).  fp32, float atomics (not bit-reproducible between runs). */
+size_t dyn_net_train_workspace_bytes(int kind, int R, int S, int V);
+size_t dyn_net_backward_scratch_bytes(int kind, int R, int S, int V);
+int dyn_net_dynamic_train_forward(dyn_net_t net, const float* pts, const float* rgb_feat, const float* ray_dir,
+                                  const float* mask, float time, int R, int S, int V, float* raw, void* saved,
+                                  size_t saved_bytes, void* stream);
+int dyn_net_dynamic_backward(dyn_net_t net, const float* pts, const float* mask, int R, int S, int V,
+                             const float* d_raw, void* saved, size_t saved_bytes, void* scratch,
+                             size_t scratch_bytes, float* d_params, float* d_rgb_feat, float* d_pts, void* stream);
+int dyn_net_static_train_forward(dyn_net_t net, const float* pts, const float* ref_rays, const float* src_rays,
+                                 const float* rgb_feat, const float* ray_diff, const float* mask, int R, int S,
+                                 int V, float* raw, void* saved, size_t saved_bytes, void* stream);
+int dyn_net_static_backward(dyn_net_t net, const float* rgb_feat, const float* ray_diff, int R, int S, int V,
+                            const float* d_raw, void* saved, size_t saved_bytes, void* scratch,
+                            size_t scratch_bytes, float* d_params, float* d_rgb_feat, void* stream);
+
+/* Smaller pieces of the training step:
+ * dyn_composite_vanilla_backward: raw2outputs_vanilla (render_ray.py:134-211).  g_rays [R,5] = d/d(rgb, depth,
+ *   mask(ignored)), g_samples [2,R,S] = d/d(weights, alpha) or NULL -> g_raw [R,S,4].  S <= 256.
+ * dyn_traj_combine(_backward): compute_traj_pts and the displacements built from it (render_ray.py:361-369,
+ *   :462-500, :1101-1176): out[i,p,:] = (base ? base[p,:] : 0) + sum_k coeff[p, axis*nb + k] * D[i,k]; D [n,nb]
+ *   (DEVICE; rows = differences of DCT basis rows), coeff [P,3*nb], base [P,3] or NULL, out [n,P,3].  The backward
+ *   writes g_coeff [P,3*nb] and / or g_base [P,3] (either may be NULL).
+ * dyn_flow_backward: compute_optical_flow (render_ray.py:333-358) -> g_weights [R,S], g_pts_seq [n_flow,R,S,3]
+ *   (either may be NULL).  S <= 256. */
+int dyn_composite_vanilla_backward(const float* raw, const float* z_vals, const float* g_rays,
+                                   const float* g_samples, int R, int S, float* g_raw, void* stream);
+int dyn_traj_combine(const float* coeff, const float* D, const float* base, int n, int nb, int P, float* out,
+                     void* stream);
+int dyn_traj_combine_backward(const float* g_out, const float* D, int n, int nb, int P, float* g_coeff,
+                              float* g_base, void* stream);
+int dyn_flow_backward(const float* weights, const float* pts_seq, const float* src_cams, const float* g_flows,
+                      int n_flow, int R, int S, float* g_weights, float* g_pts_seq, void* stream);
+
 /* ---- f1: 2-D feature encoder, ResNet.forward as the reference runs it (feature_network.py:302-311) ----
  * conv 7x7 stride 2 (reflect) -> InstanceNorm -> ReLU -> layer1 (3 BasicBlocks, the first with stride 2)
  * -> 1x1 conv -> coarse (channels 0..31) | fine (channels 32..63).  images [N,3,H,W] fp32;
