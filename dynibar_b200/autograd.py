@@ -112,7 +112,7 @@ class _MotionMLP(torch.autograd.Function):
   def forward(ctx, xyzt, module, *params):
     from dynibar_b200 import weights
     dev = dev_of(xyzt)
-    net = weights.packed_of(module, dev)
+    net = weights.packed_of(module, dev, light=True)
     x = f32c(xyzt.detach()).reshape(-1, 4)
     N = x.shape[0]
     out = torch.empty(N, 3 * net.num_basis, device=dev)
@@ -172,7 +172,7 @@ class _NetDynamic(torch.autograd.Function):
   def forward(ctx, pts, rgb_feat, ray_dir, mask, time, module, *params):
     from dynibar_b200 import weights, _lib
     dev = dev_of(pts)
-    net = weights.packed_of(module, dev)
+    net = weights.packed_of(module, dev, light=True)
     R, S, V = rgb_feat.shape[:3]
     p, f, rd, mk = f32c(pts), f32c(rgb_feat), f32c(ray_dir), f32c(mask)
     raw = torch.empty(R, S, 4, device=dev)
@@ -218,7 +218,7 @@ class _NetStatic(torch.autograd.Function):
   def forward(ctx, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask, module, *params):
     from dynibar_b200 import weights, _lib
     dev = dev_of(pts)
-    net = weights.packed_of(module, dev)
+    net = weights.packed_of(module, dev, light=True)
     R, S, V = rgb_feat.shape[:3]
     f, rd, mk = f32c(rgb_feat), f32c(ray_diff), f32c(mask)
     raw = torch.empty(R, S, 4, device=dev)
