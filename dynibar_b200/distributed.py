@@ -85,3 +85,30 @@ def render_frame_sharded(render_fn, ray_batch, group=None, dst=0):
   if world == 1:
     return px
   return gather_pixels(px, n, dst=dst, group=group)
+
+
+def allreduce_gradients(params, group=None, average=True):
+  """Training (BASELINE config 3): every rank renders its share of the N_rand rays and the gradients
+  of the ~1.6 M parameters are summed (averaged) with ONE all-reduce per step over a flat bucket -- the reference
+  never all-reduces (train.py:769-774 creates a process group but wraps nothing in DDP).  `params`: iterable of
+  tensors whose .grad to reduce in place (parameters that received no gradient on this rank contribute zeros).
+  Returns the number of elements reduced."""
+  params = [p for p in params if p.requires_grad]
+  if not params:
+    return 0
+  world = dist.get_world_size(group) if dist.is_initialized() else 1
+  for p in params:
+    if p.grad is None:
+      p.grad = torch.zeros_like(p)
+  if world == 1:
+    return sum(p.numel() for p in params)
+  flat = torch.cat([p.grad.reshape(-1) for p in params])
+  dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+  if average:
+    flat /= world
+  o = 0
+  for p in params:
+    n = p.numel()
+    p.grad.copy_(flat[o:o + n].view_as(p.grad))
+    o += n
+  return o

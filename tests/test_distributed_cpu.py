@@ -77,3 +77,42 @@ def test_shard_bounds_cover_all_rays():
       assert prev == n
       sizes = [dd.shard_bounds(n, r, w)[1] - dd.shard_bounds(n, r, w)[0] for r in range(w)]
       assert max(sizes) - min(sizes) <= 1
+
+
+def _grad_worker(rank, world, port, q):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  torch.manual_seed(0)
+  net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ELU(), torch.nn.Linear(7, 3))
+  unused = torch.nn.Parameter(torch.ones(4))  # receives no gradient on any rank
+  g = torch.Generator().manual_seed(1)
+  x, y = torch.randn(10, 5, generator=g), torch.randn(10, 3, generator=g)
+  lo, hi = dd.shard_bounds(10, rank, world)
+  # sum-of-squares loss over this rank's rows; averaging the ranks' gradients = the full-batch gradient / world
+  ((net(x[lo:hi]) - y[lo:hi]) ** 2).sum().backward()
+  n = dd.allreduce_gradients(list(net.parameters()) + [unused])
+  assert n == sum(p.numel() for p in net.parameters()) + 4
+  if rank == 0:
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ELU(), torch.nn.Linear(7, 3))
+    ref.load_state_dict(net.state_dict())
+    ((ref(x) - y) ** 2).sum().backward()
+    ok = all(torch.allclose(p.grad * world, q_.grad, rtol=1e-5, atol=1e-6)
+             for p, q_ in zip(net.parameters(), ref.parameters()))
+    q.put(ok and bool((unused.grad == 0).all()))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_full_batch():
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  ok = q.get(timeout=120)
+  for p in procs:
+    p.join(timeout=120)
+    assert p.exitcode == 0
+  assert ok
