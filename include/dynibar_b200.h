@@ -306,6 +306,15 @@ int dyn_traj_combine_backward(const float* g_out, const float* D, int n, int nb,
 int dyn_flow_backward(const float* weights, const float* pts_seq, const float* src_cams, const float* g_flows,
                       int n_flow, int R, int S, float* g_weights, float* g_pts_seq, void* stream);
 
+/* Unit-test hooks of the tensor-core training products (csrc/train_tc.cu; bf16 operands, fp32 accumulation):
+ * dyn_debug_tc_grad_w: dW[out,width] += dz[rows,out]^T (x[rows,width] * kscale[rows] or 1); out, width <= 256.
+ * dyn_debug_tc_grad_in: din[rows,width] = dz[rows,out] W[out, 0:width] (W row-major with ldw columns). */
+int dyn_debug_tc_grad_w(const float* dz, int lddz, int out, int rows, const float* x, int ldx, int width,
+                        const float* kscale, float* dW, int ldw, void* stream);
+int dyn_debug_tc_grad_in(const float* dz, int lddz, int out, int rows, const float* W, int ldw, int width,
+                         float* din, int ldd, void* scratch, size_t scratch_bytes, void* stream);
+size_t dyn_debug_tc_grad_in_scratch_bytes(void);
+
 /* ---- f1: 2-D feature encoder, ResNet.forward as the reference runs it (feature_network.py:302-311) ----
  * conv 7x7 stride 2 (reflect) -> InstanceNorm -> ReLU -> layer1 (3 BasicBlocks, the first with stride 2)
  * -> 1x1 conv -> coarse (channels 0..31) | fine (channels 32..63).  images [N,3,H,W] fp32;

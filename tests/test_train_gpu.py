@@ -243,3 +243,43 @@ def test_render_rays_mono_training_step_matches_oracle_autograd(name):
       _close("%s.%s" % (mname, k), p.grad, w[k].grad, 5e-3 if p.dim() > 1 else 2e-2)
   for i in range(3):
     _close("featmaps[%d]" % i, fd[i].grad, fo[i].grad, 5e-3)
+
+
+@pytest.mark.parametrize("rows,out,width,ldx_pad,scaled", [(5000, 128, 128, 0, False), (9000, 129, 70, 0, True),
+                                                          (4100, 256, 256, 0, False), (3000, 35, 66, 3, True),
+                                                          (20000, 64, 128, 1, False)])
+def test_tensorcore_training_products(rows, out, width, ldx_pad, scaled):
+  """csrc/train_tc.cu: dW += dZ^T X (MN-major UMMA operands, reduction over the rows) and dIn = dZ W on tcgen05
+  against fp64 products of the bf16-rounded operands (what the tensor cores multiply), fp32 accumulation."""
+  from dynibar_b200._lib import lib, ptr, check, stream
+  g = torch.Generator().manual_seed(rows + out)
+  dz = torch.randn(rows, out, generator=g)
+  ldx = width + ldx_pad
+  xfull = torch.randn(rows, ldx, generator=g)
+  sc = torch.rand(rows, generator=g) + 0.5 if scaled else None
+  r16 = lambda t: t.to(torch.bfloat16).double()
+  xs = xfull[:, :width] * sc[:, None] if scaled else xfull[:, :width]
+  want_w = r16(dz).t() @ r16(xs)
+  dzd, xd = dz.to(DEV), xfull.to(DEV)
+  dW = torch.zeros(out, width + 2, device=DEV)  # leading dimension larger than the width
+  with torch.cuda.device(DEV):
+    check(lib.dyn_debug_tc_grad_w(ptr(dzd), out, out, rows, ptr(xd), ldx, width,
+                                  ptr(sc.to(DEV)) if scaled else None, ptr(dW), width + 2, stream()))
+  got_w = dW[:, :width].cpu().double()
+  assert (dW[:, width:] == 0).all()
+  err = (got_w - want_w).norm() / want_w.norm()
+  assert err < 2e-5, ("grad_w", err.item())
+  # dIn = dZ W[:, :width] with W [out, ldw]
+  if width >= 16 and out >= 16:
+    ldw = width + 5
+    W = torch.randn(out, ldw, generator=g) * 0.1
+    want_in = r16(dz) @ r16(W[:, :width])
+    nb = int(lib.dyn_debug_tc_grad_in_scratch_bytes())
+    scratch = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    din = torch.full((rows, width + 1), 7.0, device=DEV)
+    with torch.cuda.device(DEV):
+      check(lib.dyn_debug_tc_grad_in(ptr(dzd), out, out, rows, ptr(W.to(DEV)), ldw, width, ptr(din), width + 1,
+                                     scratch.data_ptr(), nb, stream()))
+    assert (din[:, width] == 7.0).all()
+    err = (din[:, :width].cpu().double() - want_in).norm() / want_in.norm()
+    assert err < 2e-5, ("grad_in", err.item())
