@@ -109,17 +109,19 @@ def project_gather(xyz_st, xyz, query_camera, train_imgs, train_cameras, featmap
 
 class _MotionMLP(torch.autograd.Function):
   @staticmethod
-  def forward(ctx, xyzt, module, *params):
+  def forward(ctx, xyzt, module, prec, *params):
     from dynibar_b200 import weights
     dev = dev_of(xyzt)
-    net = weights.packed_of(module, dev, light=True)
+    net = weights.packed_of(module, dev, level=1 if prec else 0)
+    ctx.prec = prec
     x = f32c(xyzt.detach()).reshape(-1, 4)
     N = x.shape[0]
     out = torch.empty(N, 3 * net.num_basis, device=dev)
     nbytes = int(lib.dyn_motion_train_workspace_bytes(N))
     saved = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-      check(lib.dyn_motion_mlp_train_forward(net.handle, ptr(x), N, ptr(out), saved.data_ptr(), nbytes, stream()))
+      check(lib.dyn_motion_mlp_train_forward(net.handle, ptr(x), N, ptr(out), saved.data_ptr(), nbytes, prec,
+                                             stream()))
     ctx.net, ctx.ws, ctx.nbytes, ctx.x = net, saved, nbytes, x
     ctx.in_shape = xyzt.shape
     ctx.shapes = [p.shape for p in params]
@@ -134,7 +136,7 @@ class _MotionMLP(torch.autograd.Function):
     d_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
     with torch.cuda.device(x.device):
       check(lib.dyn_motion_mlp_backward(net.handle, ptr(x), ptr(gc), N, ctx.ws.data_ptr(), ctx.nbytes,
-                                        ptr(d_params), ptr(d_x) if d_x is not None else None, stream()))
+                                        ptr(d_params), ptr(d_x) if d_x is not None else None, ctx.prec, stream()))
     grads, o = [], 0
     for shp in ctx.shapes:  # state_dict order == parameters() order == the blob's order (weights.py)
       n = 1
@@ -142,14 +144,23 @@ class _MotionMLP(torch.autograd.Function):
         n *= d
       grads.append(d_params[o:o + n].reshape(shp))
       o += n
-    return (d_x.reshape(ctx.in_shape) if d_x is not None else None, None) + tuple(grads)
+    return (d_x.reshape(ctx.in_shape) if d_x is not None else None, None, None) + tuple(grads)
 
 
-def motion_mlp(module, xyzt):
-  """Differentiable MotionMLP.forward on [...,4] rows; honours `sf_mag_div` like render_ray.motion_mlp_forward."""
+def _prec_code(precision):
+  """None -> the library-wide setting of render_ray (`set_precision` / `precision_scope`)."""
+  from dynibar_b200 import render_ray, _lib
+  if precision is None:
+    return render_ray._prec()
+  return {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
+
+
+def motion_mlp(module, xyzt, precision=None):
+  """Differentiable MotionMLP.forward on [...,4] rows; honours `sf_mag_div` like render_ray.motion_mlp_forward.
+  precision "bf16": the products run on tcgen05 (bf16 operands, fp32 accumulation / master weights)."""
   from dynibar_b200 import weights
   m = weights.de_parallel(module)
-  out = _MotionMLP.apply(xyzt, module, *m.parameters())
+  out = _MotionMLP.apply(xyzt, module, _prec_code(precision), *m.parameters())
   div = float(getattr(m, "sf_mag_div", 1.0))
   return out / div if div != 1.0 else out
 
@@ -169,10 +180,11 @@ def _split_param_grads(d_params, shapes):
 
 class _NetDynamic(torch.autograd.Function):
   @staticmethod
-  def forward(ctx, pts, rgb_feat, ray_dir, mask, time, module, *params):
+  def forward(ctx, pts, rgb_feat, ray_dir, mask, time, module, prec, *params):
     from dynibar_b200 import weights, _lib
     dev = dev_of(pts)
-    net = weights.packed_of(module, dev, light=True)
+    net = weights.packed_of(module, dev, level=1 if prec else 0)
+    ctx.prec = prec
     R, S, V = rgb_feat.shape[:3]
     p, f, rd, mk = f32c(pts), f32c(rgb_feat), f32c(ray_dir), f32c(mask)
     raw = torch.empty(R, S, 4, device=dev)
@@ -180,7 +192,7 @@ class _NetDynamic(torch.autograd.Function):
     saved = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
       check(lib.dyn_net_dynamic_train_forward(net.handle, ptr(p), ptr(f), ptr(rd), ptr(mk), float(time), R, S, V,
-                                              ptr(raw), saved.data_ptr(), nbytes, stream()))
+                                              ptr(raw), saved.data_ptr(), nbytes, prec, stream()))
     ctx.net, ctx.ws, ctx.nbytes, ctx.p, ctx.mk, ctx.dims = net, saved, nbytes, p, mk, (R, S, V)
     ctx.shapes = [q.shape for q in params]
     return raw
@@ -200,25 +212,27 @@ class _NetDynamic(torch.autograd.Function):
       check(lib.dyn_net_dynamic_backward(net.handle, ptr(ctx.p), ptr(ctx.mk), R, S, V, ptr(g), ctx.ws.data_ptr(),
                                          ctx.nbytes, scratch.data_ptr(), sbytes, ptr(d_params),
                                          ptr(d_feat) if d_feat is not None else None,
-                                         ptr(d_pts) if d_pts is not None else None, stream()))
+                                         ptr(d_pts) if d_pts is not None else None, ctx.prec, stream()))
     ctx.ws = None
-    return (d_pts, d_feat, None, None, None, None) + tuple(_split_param_grads(d_params, ctx.shapes))
+    return (d_pts, d_feat, None, None, None, None, None) + tuple(_split_param_grads(d_params, ctx.shapes))
 
 
-def net_dynamic(module, pts, rgb_feat, ray_dir, mask, time):
-  """Differentiable DynibarDynamic.forward -> raw [R,S,4] (fp32 kernels)."""
+def net_dynamic(module, pts, rgb_feat, ray_dir, mask, time, precision=None):
+  """Differentiable DynibarDynamic.forward -> raw [R,S,4].  precision "fp32": SIMT products; "bf16": the large
+  products on tcgen05 (bf16 operands, fp32 accumulation, master weights and gradients); glue always fp32."""
   from dynibar_b200 import weights
   m = weights.de_parallel(module)
   t = float(time.reshape(-1)[0]) if torch.is_tensor(time) else float(time)
-  return _NetDynamic.apply(pts, rgb_feat, ray_dir, mask, t, module, *m.parameters())
+  return _NetDynamic.apply(pts, rgb_feat, ray_dir, mask, t, module, _prec_code(precision), *m.parameters())
 
 
 class _NetStatic(torch.autograd.Function):
   @staticmethod
-  def forward(ctx, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask, module, *params):
+  def forward(ctx, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask, module, prec, *params):
     from dynibar_b200 import weights, _lib
     dev = dev_of(pts)
-    net = weights.packed_of(module, dev, light=True)
+    net = weights.packed_of(module, dev, level=1 if prec else 0)
+    ctx.prec = prec
     R, S, V = rgb_feat.shape[:3]
     f, rd, mk = f32c(rgb_feat), f32c(ray_diff), f32c(mask)
     raw = torch.empty(R, S, 4, device=dev)
@@ -227,7 +241,7 @@ class _NetStatic(torch.autograd.Function):
     A = Args()
     with torch.cuda.device(dev):
       check(lib.dyn_net_static_train_forward(net.handle, A(pts), A(ref_rays), A(src_rays), ptr(f), ptr(rd), ptr(mk),
-                                             R, S, V, ptr(raw), saved.data_ptr(), nbytes, stream()))
+                                             R, S, V, ptr(raw), saved.data_ptr(), nbytes, prec, stream()))
     ctx.net, ctx.ws, ctx.nbytes, ctx.f, ctx.rd, ctx.dims = net, saved, nbytes, f, rd, (R, S, V)
     ctx.shapes = [q.shape for q in params]
     return raw
@@ -245,16 +259,17 @@ class _NetStatic(torch.autograd.Function):
     with torch.cuda.device(dev):
       check(lib.dyn_net_static_backward(net.handle, ptr(ctx.f), ptr(ctx.rd), R, S, V, ptr(g), ctx.ws.data_ptr(),
                                         ctx.nbytes, scratch.data_ptr(), sbytes, ptr(d_params),
-                                        ptr(d_feat) if d_feat is not None else None, stream()))
+                                        ptr(d_feat) if d_feat is not None else None, ctx.prec, stream()))
     ctx.ws = None
-    return (None, None, None, d_feat, None, None, None) + tuple(_split_param_grads(d_params, ctx.shapes))
+    return (None, None, None, d_feat, None, None, None, None) + tuple(_split_param_grads(d_params, ctx.shapes))
 
 
-def net_static(module, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask):
-  """Differentiable DynibarStatic.forward -> raw [R,S,4] (fp32 kernels)."""
+def net_static(module, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask, precision=None):
+  """Differentiable DynibarStatic.forward -> raw [R,S,4] (precision: see net_dynamic)."""
   from dynibar_b200 import weights
   m = weights.de_parallel(module)
-  return _NetStatic.apply(pts, ref_rays, src_rays, rgb_feat, ray_diff, mask, module, *m.parameters())
+  return _NetStatic.apply(pts, ref_rays, src_rays, rgb_feat, ray_diff, mask, module, _prec_code(precision),
+                          *m.parameters())
 
 
 class _CompositeVanilla(torch.autograd.Function):

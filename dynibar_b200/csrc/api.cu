@@ -113,9 +113,26 @@ size_t dyn_net_packed_bytes(int kind) {
   }
 }
 
+size_t dyn_net_layer_images_bytes(int kind) {
+  switch (kind) {
+    case DYN_NET_DYNAMIC: return (size_t)dynamic_layout().all.packed_bytes;
+    case DYN_NET_STATIC: return (size_t)static_layout(true).all.packed_bytes;
+    case DYN_NET_MOTION: return (size_t)motion_layout(8).all.packed_bytes;
+    default: return 0;
+  }
+}
+
 int dyn_net_create(int kind, const float* params, size_t n_params, void* packed, int n_samples,
                    float shift, int anti_alias_pooling, int mask_rgb, void* stream, dyn_net_t* out) {
+  return dyn_net_create_ex(kind, params, n_params, packed, packed != nullptr ? 2 : 0, n_samples, shift,
+                           anti_alias_pooling, mask_rgb, stream, out);
+}
+
+int dyn_net_create_ex(int kind, const float* params, size_t n_params, void* packed, int pack_level, int n_samples,
+                      float shift, int anti_alias_pooling, int mask_rgb, void* stream, dyn_net_t* out) {
   DYN_CHECK_ARG(out != nullptr && params != nullptr);
+  DYN_CHECK_ARG(pack_level >= 0 && pack_level <= 2 && (pack_level == 0 || packed != nullptr));
+  if (pack_level == 0) packed = nullptr;
   dyn_net* n = (dyn_net*)calloc(1, sizeof(dyn_net));
   if (!n) return fail(DYN_E_INVALID, "out of host memory");
   n->kind = kind;
@@ -162,7 +179,7 @@ int dyn_net_create(int kind, const float* params, size_t n_params, void* packed,
                               reinterpret_cast<char*>(packed) + ll.l[i].tc, (cudaStream_t)stream);
       if (rc) { free(n); return rc; }
     }
-    {  // fused tensor-core images (per-view stage, row-local chains): packed on the host once
+    if (pack_level >= 2) {  // fused tensor-core images (per-view stage, row-local chains): packed on the host once
       float* hp = (float*)malloc(n_params * sizeof(float));
       if (!hp) { free(n); return fail(DYN_E_INVALID, "out of host memory"); }
       cudaError_t e = cudaMemcpyAsync(hp, params, n_params * sizeof(float), cudaMemcpyDeviceToHost,
@@ -291,19 +308,21 @@ int dyn_motion_mlp(dyn_net_t motion, const float* xyzt, int N, float* coeff, voi
 size_t dyn_motion_train_workspace_bytes(int N) { return motion_train_workspace(N < 0 ? 0 : N); }
 
 int dyn_motion_mlp_train_forward(dyn_net_t motion, const float* xyzt, int N, float* coeff, void* saved,
-                                 size_t saved_bytes, void* stream) {
+                                 size_t saved_bytes, int precision, void* stream) {
   DYN_CHECK_ARG(motion && motion->kind == DYN_NET_MOTION && N >= 0);
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
   if (N == 0) return DYN_OK;
   DYN_CHECK_ARG(xyzt && coeff && saved);
-  return motion_train_forward(motion, xyzt, N, coeff, saved, saved_bytes, (cudaStream_t)stream);
+  return motion_train_forward(motion, xyzt, N, coeff, saved, saved_bytes, precision, (cudaStream_t)stream);
 }
 
 int dyn_motion_mlp_backward(dyn_net_t motion, const float* xyzt, const float* d_coeff, int N, void* saved,
-                            size_t saved_bytes, float* d_params, float* d_xyzt, void* stream) {
+                            size_t saved_bytes, float* d_params, float* d_xyzt, int precision, void* stream) {
   DYN_CHECK_ARG(motion && motion->kind == DYN_NET_MOTION && N >= 0);
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
   if (N == 0) return DYN_OK;
   DYN_CHECK_ARG(xyzt && d_coeff && saved && d_params);
-  return motion_train_backward(motion, xyzt, d_coeff, N, saved, saved_bytes, d_params, d_xyzt,
+  return motion_train_backward(motion, xyzt, d_coeff, N, saved, saved_bytes, d_params, d_xyzt, precision,
                                (cudaStream_t)stream);
 }
 
@@ -341,42 +360,51 @@ size_t dyn_net_backward_scratch_bytes(int kind, int R, int S, int V) {
 
 int dyn_net_dynamic_train_forward(dyn_net_t net, const float* pts, const float* rgb_feat, const float* ray_dir,
                                   const float* mask, float time, int R, int S, int V, float* raw, void* saved,
-                                  size_t saved_bytes, void* stream) {
+                                  size_t saved_bytes, int precision, void* stream) {
   if (R == 0) return DYN_OK;
   DYN_CHECK_ARG(net && net->kind == DYN_NET_DYNAMIC && pts && rgb_feat && ray_dir && mask && raw && saved);
   DYN_CHECK_ARG(R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
-  return net_dynamic_f32(net, pts, rgb_feat, ray_dir, mask, time, R, S, V, raw, saved, saved_bytes, DYN_PREC_FP32,
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
+  if (precision == DYN_PREC_BF16 && net->packed == nullptr)
+    return fail(DYN_E_INVALID, "bf16 training needs a net created with layer images (dyn_net_create_ex, pack_level >= 1)");
+  return net_dynamic_f32(net, pts, rgb_feat, ray_dir, mask, time, R, S, V, raw, saved, saved_bytes, precision,
                          (cudaStream_t)stream, /*train=*/true);
 }
 
 int dyn_net_dynamic_backward(dyn_net_t net, const float* pts, const float* mask, int R, int S, int V,
                              const float* d_raw, void* saved, size_t saved_bytes, void* scratch,
-                             size_t scratch_bytes, float* d_params, float* d_rgb_feat, float* d_pts, void* stream) {
+                             size_t scratch_bytes, float* d_params, float* d_rgb_feat, float* d_pts, int precision,
+                             void* stream) {
   if (R == 0) return DYN_OK;
   DYN_CHECK_ARG(net && net->kind == DYN_NET_DYNAMIC && pts && mask && d_raw && saved && scratch && d_params);
   DYN_CHECK_ARG(R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
   return net_dynamic_backward(net, pts, nullptr, nullptr, mask, R, S, V, d_raw, saved, saved_bytes, scratch,
-                              scratch_bytes, d_params, d_rgb_feat, d_pts, (cudaStream_t)stream);
+                              scratch_bytes, d_params, d_rgb_feat, d_pts, precision, (cudaStream_t)stream);
 }
 
 int dyn_net_static_train_forward(dyn_net_t net, const float* pts, const float* ref_rays, const float* src_rays,
                                  const float* rgb_feat, const float* ray_diff, const float* mask, int R, int S,
-                                 int V, float* raw, void* saved, size_t saved_bytes, void* stream) {
+                                 int V, float* raw, void* saved, size_t saved_bytes, int precision, void* stream) {
   if (R == 0) return DYN_OK;
   DYN_CHECK_ARG(net && net->kind == DYN_NET_STATIC && pts && ref_rays && src_rays && rgb_feat);
   DYN_CHECK_ARG(ray_diff && mask && raw && saved && R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
+  if (precision == DYN_PREC_BF16 && net->packed == nullptr)
+    return fail(DYN_E_INVALID, "bf16 training needs a net created with layer images (dyn_net_create_ex, pack_level >= 1)");
   return net_static_f32(net, pts, ref_rays, src_rays, rgb_feat, ray_diff, mask, R, S, V, raw, saved, saved_bytes,
-                        DYN_PREC_FP32, (cudaStream_t)stream, /*train=*/true);
+                        precision, (cudaStream_t)stream, /*train=*/true);
 }
 
 int dyn_net_static_backward(dyn_net_t net, const float* rgb_feat, const float* ray_diff, int R, int S, int V,
                             const float* d_raw, void* saved, size_t saved_bytes, void* scratch,
-                            size_t scratch_bytes, float* d_params, float* d_rgb_feat, void* stream) {
+                            size_t scratch_bytes, float* d_params, float* d_rgb_feat, int precision, void* stream) {
   if (R == 0) return DYN_OK;
   DYN_CHECK_ARG(net && net->kind == DYN_NET_STATIC && rgb_feat && ray_diff && d_raw && saved && scratch && d_params);
   DYN_CHECK_ARG(R >= 0 && S >= 1 && V >= 1 && V <= kMaxViews);
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
   return net_static_backward(net, rgb_feat, ray_diff, R, S, V, d_raw, saved, saved_bytes, scratch, scratch_bytes,
-                             d_params, d_rgb_feat, (cudaStream_t)stream);
+                             d_params, d_rgb_feat, precision, (cudaStream_t)stream);
 }
 
 }  // extern "C"

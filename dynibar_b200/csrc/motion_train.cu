@@ -18,6 +18,7 @@
 // autograd through the oracle.
 #include "common.cuh"
 #include "linear_f32.cuh"
+#include "linear_tc.cuh"
 #include "nets.cuh"
 #include "train_gemm.cuh"
 
@@ -178,6 +179,7 @@ struct TrainBufs {
   float* gb;       // [N,256] gradient pong
   float* gw;       // [N,388] dIn of layer 5 (cat([x0, out_4])); reused for the [N,132] dIn of layer 0
   float* gx0;      // [N,132] gradient of x0 through the skip connection
+  float* img;      // transposed weight image of the tensor-core dIn product
 };
 
 size_t train_alloc(char* base, long long N, TrainBufs* t) {
@@ -194,6 +196,7 @@ size_t train_alloc(char* base, long long N, TrainBufs* t) {
   t->gb = take((size_t)N * 256);
   t->gw = take((size_t)N * 388);
   t->gx0 = take((size_t)N * 132);
+  t->img = take(tc_grad_in_scratch_bytes() / sizeof(float));
   return off;
 }
 
@@ -205,7 +208,9 @@ size_t motion_train_workspace(long long N) {
 }
 
 int motion_train_forward(const dyn_net* n, const float* xyzt, long long N, float* coeff, void* ws,
-                         size_t ws_bytes, cudaStream_t st) {
+                         size_t ws_bytes, int prec, cudaStream_t st) {
+  const bool tc = prec == DYN_PREC_BF16;
+  if (tc && n->packed == nullptr) return fail(DYN_E_INVALID, "bf16 training needs a net created with layer images");
   const MotionLayout& L = n->ml;
   TrainBufs t;
   if (train_alloc((char*)ws, N, &t) > ws_bytes)
@@ -221,7 +226,8 @@ int motion_train_forward(const dyn_net* n, const float* xyzt, long long N, float
       a.seg[1] = Seg{t.out[4], 256, 256, 1};
       a.nseg = 2;
     }
-    rc = launch_linear(a, st);
+    rc = (tc && N >= 128) ? launch_linear_tc(a, reinterpret_cast<const char*>(n->packed) + l.tc, st)
+                          : launch_linear(a, st);
     if (rc) return rc;
   }
   const LinearP& lc = L.coeff;
@@ -229,7 +235,8 @@ int motion_train_forward(const dyn_net* n, const float* xyzt, long long N, float
 }
 
 int motion_train_backward(const dyn_net* n, const float* xyzt, const float* d_coeff, long long N, void* ws,
-                          size_t ws_bytes, float* d_params, float* d_xyzt, cudaStream_t st) {
+                          size_t ws_bytes, float* d_params, float* d_xyzt, int prec, cudaStream_t st) {
+  const bool tc = prec == DYN_PREC_BF16;
   const MotionLayout& L = n->ml;
   TrainBufs t;
   if (train_alloc((char*)ws, N, &t) > ws_bytes)
@@ -240,10 +247,17 @@ int motion_train_backward(const dyn_net* n, const float* xyzt, const float* d_co
   // product helpers on row-major operands
   auto grad_w = [&](const float* dz, long long lddz, int out, const float* in, long long ldin, int width,
                     float* dW, long long lddw) {  // dW[out, width] += dz^T in
+    if (tc && tc_grad_w_ok(out, width, N)) return tc_grad_w(dz, lddz, out, N, in, ldin, width, nullptr, dW, lddw, st);
     GemmArgs g{dz, in, dW, out, width, N, 1, lddz, ldin, 1, lddw, 1, 0};
     return launch_gemm(g, true, st);
   };
   auto grad_in = [&](const float* dz, long long lddz, int out, const float* W, int in, float* din, long long ldd) {
+    if (tc && in <= 256 && tc_grad_in_ok(out, in, N)) return tc_grad_in(dz, lddz, out, N, W, in, in, din, ldd, t.img, st);
+    if (tc && in > 256 && tc_grad_in_ok(out, 256, N) && tc_grad_in_ok(out, in - 256, N)) {  // 388 = 256 + 132
+      int rc2 = tc_grad_in(dz, lddz, out, N, W, in, 256, din, ldd, t.img, st);
+      if (rc2) return rc2;
+      return tc_grad_in(dz, lddz, out, N, W + 256, in, in - 256, din + 256, ldd, t.img, st);
+    }
     GemmArgs g{dz, W, din, N, in, out, lddz, 1, in, 1, ldd, 0, 0};  // din[N, in] = dz[N, out] W[out, in]
     return launch_gemm(g, false, st);
   };

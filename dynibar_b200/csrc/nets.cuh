@@ -43,9 +43,9 @@ int motion_embed(const float* xyzt, long long N, float* x0, cudaStream_t st);
 void motion_freqs(float f[16]);
 size_t motion_train_workspace(long long N);
 int motion_train_forward(const dyn_net* n, const float* xyzt, long long N, float* coeff, void* ws,
-                         size_t ws_bytes, cudaStream_t st);
+                         size_t ws_bytes, int prec, cudaStream_t st);
 int motion_train_backward(const dyn_net* n, const float* xyzt, const float* d_coeff, long long N, void* ws,
-                          size_t ws_bytes, float* d_params, float* d_xyzt, cudaStream_t st);
+                          size_t ws_bytes, float* d_params, float* d_xyzt, int prec, cudaStream_t st);
 
 // training backward of the two aggregation nets (nets_train.cu); the forward is net_*_f32(..., train = true)
 size_t net_train_workspace(int kind, int R, int S, int V);
@@ -53,9 +53,9 @@ size_t net_backward_scratch(int kind, int R, int S, int V);
 int net_dynamic_backward(const dyn_net* n, const float* pts, const float* rgb_feat, const float* ray_dir,
                          const float* mask, int R, int S, int V, const float* d_raw, void* ws, size_t ws_bytes,
                          void* scratch, size_t scratch_bytes, float* d_params, float* d_rgb_feat, float* d_pts,
-                         cudaStream_t st);
+                         int prec, cudaStream_t st);
 int net_static_backward(const dyn_net* n, const float* rgb_feat, const float* ray_diff, int R, int S, int V,
                         const float* d_raw, void* ws, size_t ws_bytes, void* scratch, size_t scratch_bytes,
-                        float* d_params, float* d_rgb_feat, cudaStream_t st);
+                        float* d_params, float* d_rgb_feat, int prec, cudaStream_t st);
 
 }  // namespace dyn

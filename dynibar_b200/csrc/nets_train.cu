@@ -518,10 +518,14 @@ struct Prod {
   cudaStream_t st;
   const float* prm;
   float* dprm;
+  bool tc;      // large products on tcgen05 (train_tc.cu)
+  void* img;    // scratch of tc_grad_in
   // dW[out, width] (leading dimension ldw, column offset applied by the caller) += dz^T in;
   // in[(row / bdiv) * ldin + c], optionally scaled per row
   int grad_w(const float* dz, long long lddz, int out, long long rows, const float* in, long long ldin, int width,
              float* dW, long long ldw, long long bdiv = 1, const float* kscale = nullptr) const {
+    if (tc && bdiv == 1 && tc_grad_w_ok(out, width, rows))
+      return tc_grad_w(dz, lddz, out, rows, in, ldin, width, kscale, dW, ldw, st);
     GemmArgs g{dz, in, dW, out, width, rows, 1, lddz, ldin, 1, ldw, 1, 0};
     g.bdiv = bdiv;
     g.kscale = kscale;
@@ -530,6 +534,8 @@ struct Prod {
   // din[rows, width] (+)= dz[rows, out] W[out, coloff : coloff + width]   (W row-major with ldw columns)
   int grad_in(const float* dz, long long lddz, int out, long long rows, const float* W, long long ldw, int width,
               float* din, long long ldd, bool accumulate = false) const {
+    if (tc && !accumulate && tc_grad_in_ok(out, width, rows))
+      return tc_grad_in(dz, lddz, out, rows, W, ldw, width, din, ldd, img, st);
     GemmArgs g{dz, W, din, rows, width, out, lddz, 1, ldw, 1, ldd, accumulate ? 1 : 0, 0};
     return launch_gemm(g, false, st);
   }
@@ -569,6 +575,7 @@ struct BwdBufs {
   float *pA, *pB, *pC, *pD, *pE, *pF, *pG, *pMV, *pX, *pY, *p64, *p33, *p3, *pS;  // per point
   float *rA, *rB;                                                  // per ray
   float* small;
+  float* img;                                                      // tc_grad_in weight image
 };
 
 size_t bwd_alloc(Bump& b, bool st_net, int R, int S, int V, BwdBufs* q) {
@@ -586,6 +593,7 @@ size_t bwd_alloc(Bump& b, bool st_net, int R, int S, int V, BwdBufs* q) {
   q->pY = b.f(P * 256); q->p64 = b.f(P * 64); q->p33 = b.f(P * 33); q->p3 = b.f(P * 3); q->pS = b.f(P);
   q->rA = b.f((long long)R * 128); q->rB = b.f((long long)R * 2 * kF);
   q->small = b.f(64);
+  q->img = b.f(tc_grad_in_scratch_bytes() / sizeof(float));
   return b.off;
 }
 
@@ -698,7 +706,7 @@ size_t net_backward_scratch(int kind, int R, int S, int V) {
 int net_dynamic_backward(const dyn_net* n, const float* pts, const float* rgb_feat, const float* ray_dir,
                          const float* mask, int R, int S, int V, const float* d_raw, void* ws, size_t ws_bytes,
                          void* scratch, size_t scratch_bytes, float* d_params, float* d_rgb_feat, float* d_pts,
-                         cudaStream_t st) {
+                         int prec, cudaStream_t st) {
   (void)rgb_feat; (void)ray_dir;
   const DynamicLayout& L = n->dl;
   const long long P = (long long)R * S, M = P * V;
@@ -708,7 +716,7 @@ int net_dynamic_backward(const dyn_net* n, const float* pts, const float* rgb_fe
   Bump b2{(char*)scratch, 0};
   BwdBufs q;
   if (bwd_alloc(b2, false, R, S, V, &q) > scratch_bytes) return fail(DYN_E_WORKSPACE, "net backward: scratch too small");
-  const Prod pr{st, n->params, d_params};
+  const Prod pr{st, n->params, d_params, prec == DYN_PREC_BF16, q.img};
   const float* prm = n->params;
   float* dprm = d_params;
   // heads (mlp_network.py:294-315)
@@ -757,7 +765,7 @@ int net_dynamic_backward(const dyn_net* n, const float* pts, const float* rgb_fe
 
 int net_static_backward(const dyn_net* n, const float* rgb_feat, const float* ray_diff, int R, int S, int V,
                         const float* d_raw, void* ws, size_t ws_bytes, void* scratch, size_t scratch_bytes,
-                        float* d_params, float* d_rgb_feat, cudaStream_t st) {
+                        float* d_params, float* d_rgb_feat, int prec, cudaStream_t st) {
   const StaticLayout& L = n->sl;
   const long long P = (long long)R * S, M = P * V;
   Bump b{(char*)ws, 0};
@@ -766,7 +774,7 @@ int net_static_backward(const dyn_net* n, const float* rgb_feat, const float* ra
   Bump b2{(char*)scratch, 0};
   BwdBufs q;
   if (bwd_alloc(b2, true, R, S, V, &q) > scratch_bytes) return fail(DYN_E_WORKSPACE, "net backward: scratch too small");
-  const Prod pr{st, n->params, d_params};
+  const Prod pr{st, n->params, d_params, prec == DYN_PREC_BF16, q.img};
   const float* prm = n->params;
   float* dprm = d_params;
   // blending head (mlp_network.py:508-526)

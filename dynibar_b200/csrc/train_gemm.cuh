@@ -24,4 +24,15 @@ int launch_gemm(GemmArgs a, bool split_k, cudaStream_t st);
 // db[c] += sum_r g[r * ldg + c], c < width
 int launch_colsum(const float* g, long long ldg, int width, long long N, float* db, cudaStream_t st);
 
+// tensor-core versions (train_tc.cu; bf16 operands, fp32 accumulation); *_ok tells whether a shape is supported
+bool tc_grad_w_ok(int out, int width, long long rows);
+bool tc_grad_in_ok(int out, int width, long long rows);
+size_t tc_grad_in_scratch_bytes();
+// dW[out, width] (ld ldw) += dz[rows, out]^T (x[rows, width] * kscale[rows])
+int tc_grad_w(const float* dz, long long lddz, int out, long long rows, const float* x, long long ldx, int width,
+              const float* kscale, float* dW, long long ldw, cudaStream_t st);
+// din[rows, width] (ld ldd) = dz[rows, out] W[out, 0:width] (W row-major, ldw columns; pass W + column offset)
+int tc_grad_in(const float* dz, long long lddz, int out, long long rows, const float* W, long long ldw, int width,
+               float* din, long long ldd, void* img_scratch, cudaStream_t st);
+
 }  // namespace dyn

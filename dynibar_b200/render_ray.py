@@ -9,7 +9,7 @@ reference): `render_rays_mv` (render_ray.py:600), `render_rays_mono` (:870),
 All math runs in `csrc/` kernels through the C ABI (include/dynibar_b200.h);
 this file only allocates tensors and sequences calls.  `render_rays_mono` is
 differentiable (training): when gradients are enabled and the
-model's parameters or the feature maps require grad it runs the fp32 training
+model's parameters or the feature maps require grad it runs the training
 path (`_render_mono_train`, autograd Functions of dynibar_b200/autograd.py over
 the backward kernels).  `render_rays_mv` is the evaluation path (the reference
 calls it under no_grad) and refuses inputs that require grad.
@@ -604,8 +604,9 @@ def render_rays_mono(frame_idx, time_embedding, time_offset, ray_batch, model, f
   maps that require grad the differentiable fp32 training path runs (`_render_mono_train`); otherwise
   the forward-only kernels (fused tcgen05 path in bf16 mode) under no_grad."""
   if _wants_grad(model, featmaps):
-    return _render_mono_train(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, N_samples,
-                              args, inv_uniform, det, is_train, num_vv, jitter)
+    with precision_scope(precision):
+      return _render_mono_train(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, N_samples,
+                                args, inv_uniform, det, is_train, num_vv, jitter)
   with torch.no_grad(), precision_scope(precision):
     t = _scalar(time_embedding[0].float())
     ray_batch, hb = _with_host_copies(ray_batch, model, ("trajectory_basis",))
@@ -676,9 +677,11 @@ def _cross_time(ray_batch, feat_anchor, pts, z, aux, ref_idx, anc_idx, t_anc, an
 def _render_mono_train(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, N_samples, args,
                        inv_uniform, det, is_train, num_vv, jitter):
   """render_rays_mono (render_ray.py:870-1277) with autograd: the same sequence as the reference, every stage a
-  `torch.autograd.Function` over the fp32 forward/backward kernels (dynibar_b200/autograd.py).  Gradients reach
+  `torch.autograd.Function` over the forward/backward kernels (dynibar_b200/autograd.py).  Gradients reach
   the parameters of motion_mlp / net_coarse_dy / net_coarse_st and the feature maps.  torch itself only
-  concatenates the time column, zeroes the last samples' coefficients, slices and detaches."""
+  concatenates the time column, zeroes the last samples' coefficients, slices and detaches.  Precision (the
+  library-wide setting / `precision=`): "bf16" runs the products of the three networks, forward and backward, on
+  tcgen05 (bf16 operands, fp32 accumulation, fp32 master weights and gradients); "fp32" = SIMT products."""
   from dynibar_b200 import autograd as ag
   t = _scalar(time_embedding[0].float())
   rb, hb = _with_host_copies(ray_batch, model, ("trajectory_basis",))

@@ -32,19 +32,21 @@ def flatten(module):
 class PackedNet(object):
   """Owns the device blob(s) and the dyn_net_t handle."""
 
-  def __init__(self, module, device, light=False):
-    """`light`: fp32 parameters only, no tensor-core operand images (the fp32 training path re-packs after every
-    optimizer step and never runs the fused kernels)."""
+  def __init__(self, module, device, level=2):
+    """`level`: 2 = every tensor-core operand image (inference: fused kernels), 1 = per-layer images only (bf16
+    training: rebuilt by device kernels after every optimizer step), 0 = fp32 parameters only (fp32 training)."""
     m = de_parallel(module)
     self.kind = _KIND[type(m).__name__]
+    self.level = level
     self.blob = flatten(m).to(device).contiguous()
-    nbytes = _lib.lib.dyn_net_packed_bytes(self.kind)
-    self.packed = None if light else torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+    nbytes = (_lib.lib.dyn_net_packed_bytes(self.kind) if level == 2
+              else _lib.lib.dyn_net_layer_images_bytes(self.kind))
+    self.packed = None if level == 0 else torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
     h = C.c_void_p()
     with torch.cuda.device(device):
-      _lib.check(_lib.lib.dyn_net_create(
+      _lib.check(_lib.lib.dyn_net_create_ex(
           self.kind, self.blob.data_ptr(), self.blob.numel(),
-          None if light else self.packed.data_ptr(),
+          None if level == 0 else self.packed.data_ptr(), level,
           int(getattr(m, "n_samples", 0)), float(getattr(m, "shift", 0.0)),
           int(bool(getattr(m, "anti_alias_pooling", 0))), int(bool(getattr(m, "mask_rgb", 0))),
           _lib.stream(), C.byref(h)))
@@ -63,14 +65,14 @@ def pack(module, device):
   return PackedNet(module, device)
 
 
-def packed_of(module, device, light=False):
+def packed_of(module, device, level=2):
   """Cached PackedNet of a network module; re-packed when any parameter's
-  storage or `_version` changes (optimizer steps, load_state_dict).  `light` (training): see PackedNet."""
+  storage or `_version` changes (optimizer steps, load_state_dict).  `level`: see PackedNet."""
   m = de_parallel(module)
   key = (tuple((p.data_ptr(), p._version) for p in m.parameters()), str(device))
-  slot = "_dyn_pack_cache_light" if light else "_dyn_pack_cache"
+  slot = "_dyn_pack_cache_%d" % level if level != 2 else "_dyn_pack_cache"
   cache = m.__dict__.get(slot)
   if cache is None or cache[0] != key:
-    cache = (key, PackedNet(m, device, light))
+    cache = (key, PackedNet(m, device, level))
     m.__dict__[slot] = cache
   return cache[1]

@@ -77,6 +77,13 @@ size_t dyn_net_packed_bytes(int kind);
 int dyn_net_create(int kind, const float* params, size_t n_params, void* packed,
                    int n_samples, float shift, int anti_alias_pooling,
                    int mask_rgb, void* stream, dyn_net_t* out);
+/* pack_level: 0 = fp32 parameters only (packed may be NULL), 1 = per-layer tensor-core images only
+ * (dyn_net_layer_images_bytes(kind) bytes: enough for the staged DYN_PREC_BF16 evaluation and the bf16 training
+ * step, cheap enough to rebuild after every optimizer step), 2 = everything (== dyn_net_create). */
+size_t dyn_net_layer_images_bytes(int kind);
+int dyn_net_create_ex(int kind, const float* params, size_t n_params, void* packed, int pack_level,
+                      int n_samples, float shift, int anti_alias_pooling, int mask_rgb, void* stream,
+                      dyn_net_t* out);
 void dyn_net_destroy(dyn_net_t net);
 
 /* ---- a2: sample_along_camera_ray, render_ray.py:67-131 -------------------
@@ -260,9 +267,9 @@ int dyn_project_gather_backward(const float* xyz_st, const float* xyz, const flo
  * fp32; split-K float atomics (not bit-reproducible between runs). */
 size_t dyn_motion_train_workspace_bytes(int N);
 int dyn_motion_mlp_train_forward(dyn_net_t motion, const float* xyzt, int N, float* coeff, void* saved,
-                                 size_t saved_bytes, void* stream);
+                                 size_t saved_bytes, int precision, void* stream);
 int dyn_motion_mlp_backward(dyn_net_t motion, const float* xyzt, const float* d_coeff, int N, void* saved,
-                            size_t saved_bytes, float* d_params, float* d_xyzt, void* stream);
+                            size_t saved_bytes, float* d_params, float* d_xyzt, int precision, void* stream);
 
 /* ---- f2: training step of the two aggregation networks (DynibarDynamic.forward, ibrnet/mlp_network.py:236-316;
  * DynibarStatic.forward, :423-527; gradients as torch.autograd produces them for those modules).
@@ -272,21 +279,25 @@ int dyn_motion_mlp_backward(dyn_net_t motion, const float* xyzt, const float* d_
  * d_params (flat, layout of the blob given to dyn_net_create; the caller zeroes it) and writes
  * d_rgb_feat [R,S,V,35] (gradient w.r.t. the gathered colours + features; NULL to skip) and, for the dynamic net,
  * d_pts [R,S,3] (through the positional encoding of ref_pts_fc; NULL to skip).  mask / ray_diff / rays / time carry
- * no gradient (the reference detaches them).  fp32, float atomics (not bit-reproducible between runs). */
+ * no gradient (the reference detaches them).  `precision`: DYN_PREC_FP32 = SIMT products; DYN_PREC_BF16 = the
+ * products of the large layers on tcgen05 (bf16 operands, fp32 accumulation, fp32 master weights / gradients; the
+ * net must have been created with layer images, dyn_net_create_ex pack_level >= 1); everything else stays fp32.
+ * Float atomics (not bit-reproducible between runs). */
 size_t dyn_net_train_workspace_bytes(int kind, int R, int S, int V);
 size_t dyn_net_backward_scratch_bytes(int kind, int R, int S, int V);
 int dyn_net_dynamic_train_forward(dyn_net_t net, const float* pts, const float* rgb_feat, const float* ray_dir,
                                   const float* mask, float time, int R, int S, int V, float* raw, void* saved,
-                                  size_t saved_bytes, void* stream);
+                                  size_t saved_bytes, int precision, void* stream);
 int dyn_net_dynamic_backward(dyn_net_t net, const float* pts, const float* mask, int R, int S, int V,
                              const float* d_raw, void* saved, size_t saved_bytes, void* scratch,
-                             size_t scratch_bytes, float* d_params, float* d_rgb_feat, float* d_pts, void* stream);
+                             size_t scratch_bytes, float* d_params, float* d_rgb_feat, float* d_pts, int precision,
+                             void* stream);
 int dyn_net_static_train_forward(dyn_net_t net, const float* pts, const float* ref_rays, const float* src_rays,
                                  const float* rgb_feat, const float* ray_diff, const float* mask, int R, int S,
-                                 int V, float* raw, void* saved, size_t saved_bytes, void* stream);
+                                 int V, float* raw, void* saved, size_t saved_bytes, int precision, void* stream);
 int dyn_net_static_backward(dyn_net_t net, const float* rgb_feat, const float* ray_diff, int R, int S, int V,
                             const float* d_raw, void* saved, size_t saved_bytes, void* scratch,
-                            size_t scratch_bytes, float* d_params, float* d_rgb_feat, void* stream);
+                            size_t scratch_bytes, float* d_params, float* d_rgb_feat, int precision, void* stream);
 
 /* Smaller pieces of the training step:
  * dyn_composite_vanilla_backward: raw2outputs_vanilla (render_ray.py:134-211).  g_rays [R,5] = d/d(rgb, depth,

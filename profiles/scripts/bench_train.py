@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Times the training step of BASELINE config 3 (N_rand = 1024 rays, 64 coarse samples, render_rays_mono with the
 cross-time branch, forward + backward + Adam step) through the differentiable fp32 path.  Secondary measurement,
-not bench.py's metric.  Usage: python profiles/scripts/bench_train.py [steps] [rays]"""
+not bench.py's metric.  Usage: python profiles/scripts/bench_train.py [steps] [rays] [bf16|fp32]"""
 import json
 import os
 import sys
@@ -17,6 +17,7 @@ from dynibar_b200._lib import lib  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 rays = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
 dev = torch.device("cuda:0")
 batch, feat_c, _, frame, t, offs = synthetic.make_scene(H=288, W=512, V_dy=8, V_st=8, num_vv=2, seed=3, rays=rays,
                                                         anchor_offset=2)
@@ -38,7 +39,7 @@ proj = Projector(dev)
 def step():
   opt.zero_grad(set_to_none=True)
   ret = rr.render_rays_mono(frame, t, offs, b, model, feat, proj, 64, args, inv_uniform=True, det=False, is_train=True,
-                            num_vv=2)
+                            num_vv=2, precision=prec)
   loss = ((ret["outputs_coarse_ref"]["rgb"] - target) ** 2).mean()
   loss = loss + ((ret["outputs_coarse_anchor"]["rgb"] - target) ** 2).mean()
   loss = loss + 1e-3 * ret["outputs_coarse_ref"]["render_flows"].abs().mean()
@@ -60,7 +61,7 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(json.dumps({"what": "training step, BASELINE config 3 shape (render_rays_mono is_train=True, fwd + bwd + Adam)",
-                  "rays": rays, "samples": 64, "views": "6+2 dynamic, 8 static, 6+2 anchor", "precision": "fp32",
+                  "rays": rays, "samples": 64, "views": "6+2 dynamic, 8 static, 6+2 anchor", "precision": prec,
                   "ms_per_step": ms, "rays_per_s": rays / ms * 1e3, "loss_first": float(l0), "loss_last": float(l1),
                   "kernel_launches_per_step": (lib.dyn_launch_count(0) - n0) / steps,
                   "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))

@@ -3,9 +3,10 @@ functions: DynibarDynamic.forward / DynibarStatic.forward (mlp_network.py:236-31
 differentiable pieces (raw2outputs_vanilla, compute_traj_pts, compute_optical_flow) and the whole
 `render_rays_mono(is_train=True)` training forward + backward (render_ray.py:870-1277).
 
-Bar: forward values rtol 2e-4; gradients 1e-3 relative in the L2 norm per tensor (fp32 kernels with a different
-summation order than ATen; ELU is C1, so there are no kink flips except the MotionMLP's ReLUs, see
-test_backward_gpu.py)."""
+Bar, precision "fp32": forward values rtol 2e-4; gradients 1e-3 relative in the L2 norm per tensor (fp32 kernels
+with a different summation order than ATen; ELU is C1, so there are no kink flips except the MotionMLP's ReLUs, see
+test_backward_gpu.py).  Precision "bf16" (products on tcgen05 with bf16 operands, everything else fp32): forward
+2e-2, gradients 5e-2 (matrices) / 1e-1 (vectors) against the same fp32 oracle."""
 
 import pytest
 import torch
@@ -52,8 +53,14 @@ def _net_inputs(R, S, V, seed):
   return g, pts, feat, mask, ray_dir
 
 
-@pytest.mark.parametrize("R,S,V", [(6, 16, 5), (3, 40, 8)])
-def test_net_dynamic_backward_matches_oracle_autograd(R, S, V):
+def _tol(prec, dim):
+  if prec == "fp32":
+    return 1e-3
+  return 5e-2 if dim > 1 else 1e-1
+
+
+@pytest.mark.parametrize("R,S,V,prec", [(6, 16, 5, "fp32"), (3, 40, 8, "fp32"), (40, 16, 8, "bf16")])
+def test_net_dynamic_backward_matches_oracle_autograd(R, S, V, prec):
   from dynibar_b200 import autograd as ag, mlp_network as nets
   torch.manual_seed(R * S + V)
   args = synthetic.make_args(1, 0)
@@ -72,17 +79,19 @@ def test_net_dynamic_backward_matches_oracle_autograd(R, S, V):
   # ---- library
   mod = mod.to(DEV).requires_grad_(True)
   pd, fd = pts.to(DEV).requires_grad_(True), feat.to(DEV).requires_grad_(True)
-  got = ag.net_dynamic(mod, pd, fd, ray_dir.to(DEV), mask.to(DEV), t)
-  torch.testing.assert_close(got.detach().cpu(), want.detach(), rtol=2e-4, atol=2e-5)
+  got = ag.net_dynamic(mod, pd, fd, ray_dir.to(DEV), mask.to(DEV), t, precision=prec)
+  ft = dict(rtol=2e-4, atol=2e-5) if prec == "fp32" else dict(rtol=2e-2, atol=5e-3)
+  torch.testing.assert_close(got.detach().cpu(), want.detach(), **ft)
   (got * (gen * torch.cat([live.expand(-1, -1, 3), live], -1)).to(DEV)).sum().backward()
   for k, p in mod.named_parameters():
-    _close(k, p.grad, w[k].grad)
-  _close("rgb_feat", fd.grad, fo.grad)
-  _close("pts", pd.grad, po.grad)
+    _close(k, p.grad, w[k].grad, _tol(prec, p.dim()))
+  _close("rgb_feat", fd.grad, fo.grad, _tol(prec, 2))
+  _close("pts", pd.grad, po.grad, _tol(prec, 2))
 
 
-@pytest.mark.parametrize("R,S,V,aa,mrgb", [(6, 16, 5, 1, 0), (3, 24, 8, 0, 1), (4, 16, 11, 1, 1)])
-def test_net_static_backward_matches_oracle_autograd(R, S, V, aa, mrgb):
+@pytest.mark.parametrize("R,S,V,aa,mrgb,prec", [(6, 16, 5, 1, 0, "fp32"), (3, 24, 8, 0, 1, "fp32"),
+                                                   (4, 16, 11, 1, 1, "fp32"), (40, 16, 8, 1, 0, "bf16")])
+def test_net_static_backward_matches_oracle_autograd(R, S, V, aa, mrgb, prec):
   from dynibar_b200 import autograd as ag, mlp_network as nets
   torch.manual_seed(R * S + V)
   args = synthetic.make_args(aa, mrgb)
@@ -108,13 +117,22 @@ def test_net_static_backward_matches_oracle_autograd(R, S, V, aa, mrgb):
   mod = mod.to(DEV).requires_grad_(True)
   fd = feat.to(DEV).requires_grad_(True)
   d = lambda x: x.to(DEV)
-  got = ag.net_static(mod, d(pts), d(ref_rays), d(src_rays), fd, d(ray_diff), d(mask))
-  torch.testing.assert_close(got.detach().cpu(), want.detach(), rtol=2e-4, atol=2e-5)
+  got = ag.net_static(mod, d(pts), d(ref_rays), d(src_rays), fd, d(ray_diff), d(mask), precision=prec)
+  ft = dict(rtol=2e-4, atol=2e-5) if prec == "fp32" else dict(rtol=2e-2, atol=5e-3)
+  torch.testing.assert_close(got.detach().cpu(), want.detach(), **ft)
   (got * d(gen * scale)).sum().backward()
   for k, p in mod.named_parameters():
-    # `s` (anti-alias pooling): a small sum of large cancelling terms, (e - min e) / (sum + 1e-8)
-    _close(k, p.grad, w[k].grad, 1e-2 if k == "s" else 1e-3)
-  _close("rgb_feat", fd.grad, fo.grad)
+    # `s` (anti-alias pooling): a small sum of large cancelling terms, (e - min e) / (sum + 1e-8): 1e-2 in fp32; with
+    # bf16 products the 0.5 % noise of d(pooling weights) is amplified by 1 / (sum + 1e-8) past the signal
+    # (profiles/r02_train.md), so only finiteness is checked there
+    if k == "s":
+      if prec == "fp32":
+        _close(k, p.grad, w[k].grad, 1e-2)
+      else:
+        assert torch.isfinite(p.grad).all()
+      continue
+    _close(k, p.grad, w[k].grad, _tol(prec, p.dim()))
+  _close("rgb_feat", fd.grad, fo.grad, _tol(prec, 2))
 
 
 def test_small_pieces_match_oracle_autograd():
@@ -185,14 +203,16 @@ _TRAIN_KEYS = {
 }
 
 
-@pytest.mark.parametrize("name", ["mono_train", "mono_train_near"])
-def test_render_rays_mono_training_step_matches_oracle_autograd(name):
+@pytest.mark.parametrize("name,prec", [("mono_train", "fp32"), ("mono_train_near", "fp32"), ("mono_train", "bf16")])
+def test_render_rays_mono_training_step_matches_oracle_autograd(name, prec):
   """The whole differentiable path: loss = sum of randomly weighted differentiable outputs of
   render_rays_mono(is_train=True); d loss / d (every parameter of motion_mlp, net_coarse_dy, net_coarse_st and the
   three feature maps) against torch autograd through the oracle."""
   from dynibar_b200 import render_ray as rr
   from dynibar_b200.projection import Projector
   cfg = dict(scenes.GOLDEN_CONFIGS[name])
+  if prec == "bf16":
+    cfg["rays"] = 96  # >= 2048 (point, view) rows per product: the tensor-core kernels take over
   batch, feat_c, _, frame, t, offs, model, args = scenes.build(cfg)
   with torch.no_grad():  # larger motion than the bench initialisation so that its gradients are well above rounding
     model.motion_mlp.coeff_linear.weight.normal_(0.0, 0.05)
@@ -216,14 +236,17 @@ def test_render_rays_mono_training_step_matches_oracle_autograd(name):
   fd = tuple(f.to(dev).requires_grad_(True) for f in feat_c)
   got = rr.render_rays_mono(frame, t, offs, synthetic.to_device(batch, dev), m_dev, fd, Projector(dev),
                             cfg["N_samples"], args, inv_uniform=cfg["inv_uniform"], det=True, is_train=True,
-                            num_vv=cfg["num_vv"])
+                            num_vv=cfg["num_vv"], precision=prec)
+  ft = dict(rtol=1e-3, atol=2e-4) if prec == "fp32" else dict(rtol=3e-2, atol=2e-2)
   for (o, k), v in gens.items():
     assert got[o][k].requires_grad, (o, k)
-    torch.testing.assert_close(got[o][k].detach().cpu(), want[o][k].detach(), rtol=1e-3, atol=2e-4,
-                               msg=lambda s: "%s/%s: %s" % (o, k, s))
+    if prec == "bf16" and k == "render_flows":
+      continue  # pixels: a bf16-sized change of the weights moves the expected point by a fraction of a pixel
+    torch.testing.assert_close(got[o][k].detach().cpu(), want[o][k].detach(),
+                               msg=lambda s: "%s/%s: %s" % (o, k, s), **ft)
   for o in ("outputs_coarse_anchor", "outputs_coarse_anchor_dy"):  # detached in the reference (:1222, :1254)
     assert not got[o]["occ_weights"].requires_grad and not got[o]["occ_weight_map"].requires_grad
-    torch.testing.assert_close(got[o]["occ_weights"].cpu(), want[o]["occ_weights"].detach(), rtol=1e-3, atol=2e-4)
+    torch.testing.assert_close(got[o]["occ_weights"].cpu(), want[o]["occ_weights"].detach(), **ft)
   assert not got["outputs_coarse_ref"]["exp_sf"].requires_grad
   sum((got[o][k] * v.to(dev)).sum() for (o, k), v in gens.items()).backward()
   for mname, w in (("net_coarse_dy", om.net_coarse_dy), ("net_coarse_st", om.net_coarse_st),
@@ -240,9 +263,18 @@ def test_render_rays_mono_training_step_matches_oracle_autograd(name):
       # (profiles/r02_train.md) -- and 2e-2 for bias / LayerNorm vectors: column sums over all rows whose terms cancel
       # to ~1e-3 of their magnitude (e.g. the blending head: sum_v d logit_v = 0 per point), so the summation order
       # shows; a wrong or missing term is an O(1) error
-      _close("%s.%s" % (mname, k), p.grad, w[k].grad, 5e-3 if p.dim() > 1 else 2e-2)
+      if prec == "fp32":
+        _close("%s.%s" % (mname, k), p.grad, w[k].grad, 5e-3 if p.dim() > 1 else 2e-2)
+      elif mname == "motion_mlp" and k.startswith("pts_linears"):
+        # ReLU network with bf16 products: pre-activations within bf16 rounding of 0 (~0.3 % of the units per layer)
+        # take the other side of the kink, each flip is an O(1) change of that unit's gradient -> sqrt(0.003) ~ 5 %
+        # in L2 at the last hidden layer, growing to ~11 % at the first (measured: profiles/r02_train.md); the smooth
+        # (ELU) aggregation nets stay at 0.2 - 0.5 %
+        _close("%s.%s" % (mname, k), p.grad, w[k].grad, 2e-1, floor=1e-5)
+      else:  # bf16 operands: 2^-9 per element, averaged over the reductions and chained through ~10 layers
+        _close("%s.%s" % (mname, k), p.grad, w[k].grad, 5e-2 if p.dim() > 1 else 1.5e-1, floor=1e-5)
   for i in range(3):
-    _close("featmaps[%d]" % i, fd[i].grad, fo[i].grad, 5e-3)
+    _close("featmaps[%d]" % i, fd[i].grad, fo[i].grad, 5e-3 if prec == "fp32" else 5e-2)
 
 
 @pytest.mark.parametrize("rows,out,width,ldx_pad,scaled", [(5000, 128, 128, 0, False), (9000, 129, 70, 0, True),
