@@ -24,7 +24,11 @@ constexpr int kWStages = 3;
 constexpr int kTileBytes = 128 * kKC * 2;      // one 128-row A sub-tile of a chunk: 16 KB
 constexpr int kABufBytes = 2 * kTileBytes;     // both tiles: 32 KB
 constexpr int kWStageBytes = 256 * kKC * 2;    // 32 KB (N up to 256)
-constexpr int kSmemBytes = 2 * kABufBytes + kWStages * kWStageBytes + 1024;
+constexpr int kSmemBytes = 2 * kABufBytes + kWStages * kWStageBytes + 1024;  // N up to 256: one CTA per SM
+// narrower layers use weight stages of their own size (Npad x 64 bf16) and two of them: two CTAs fit an SM and
+// the load / MMA / store phases of one overlap the other's
+__host__ __device__ constexpr int w_stages(int Npad) { return Npad <= 144 ? 2 : kWStages; }
+__host__ __device__ constexpr int smem_bytes(int Npad) { return 2 * kABufBytes + w_stages(Npad) * Npad * kKC * 2 + 1024; }
 
 __device__ __forceinline__ float act_f(float v, int act) {
   switch (act) {
@@ -47,11 +51,13 @@ __device__ __forceinline__ float seg_value(const TcLinArgs& a, long long row, in
   return 0.f;
 }
 
-__global__ void __launch_bounds__(288, 1) linear_tc_kernel(const __grid_constant__ TcLinArgs a) {
+__global__ void __launch_bounds__(288, 2) linear_tc_kernel(const __grid_constant__ TcLinArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const int nws = w_stages(a.Npad);                       // weight ring depth
+  const int wsb = a.Npad * kKC * 2;                       // bytes per weight stage
   uint8_t* a_buf = smem;                                  // 2 x 32 KB
-  uint8_t* w_buf = smem + 2 * kABufBytes;                 // 3 x 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kABufBytes + kWStages * kWStageBytes);
+  uint8_t* w_buf = smem + 2 * kABufBytes;                 // nws x wsb
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kABufBytes + nws * wsb);
   // bars: [0,1] a_full, [2,3] a_empty, [4..6] w_full, [7..9] w_empty, [10] acc_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
@@ -65,7 +71,7 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const __grid_constant
   if (tid == 0) {
     mbar_init(BAR(0), 256); mbar_init(BAR(1), 256);
     mbar_init(BAR(2), 1); mbar_init(BAR(3), 1);
-    for (int i = 0; i < kWStages; ++i) { mbar_init(BAR(4 + i), 1); mbar_init(BAR(7 + i), 1); }
+    for (int i = 0; i < kWStages; ++i) { mbar_init(BAR(4 + i), 1); mbar_init(BAR(7 + i), 1); }  // nws of them used
     mbar_init(BAR(10), 1);
     mbar_fence_init();
   }
@@ -85,28 +91,29 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const __grid_constant
       // ---------------- weight producer + MMA issuer ----------------
       const uint32_t idesc = idesc_bf16_f32(128, a.Npad);
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.Wp);
-      for (int c = 0; c < 2 && c < nchunks; ++c) {
+      const int ahead = nws - 1;  // chunks requested ahead of the one being multiplied
+      for (int c = 0; c < ahead && c < nchunks; ++c) {
         mbar_arrive_expect_tx(BAR(4 + c), w_chunk_bytes);
-        bulk_g2s(smem_u32(w_buf + c * kWStageBytes), wsrc + (size_t)c * w_chunk_bytes, w_chunk_bytes,
+        bulk_g2s(smem_u32(w_buf + c * wsb), wsrc + (size_t)c * w_chunk_bytes, w_chunk_bytes,
                  BAR(4 + c));
       }
       for (int kc = 0; kc < nchunks; ++kc) {
-        const int c2 = kc + 2;
+        const int c2 = kc + ahead;
         if (c2 < nchunks) {
-          const int s2 = c2 % kWStages;
-          if (c2 >= kWStages) mbar_wait(BAR(7 + s2), ((c2 / kWStages) - 1) & 1);
+          const int s2 = c2 % nws;
+          if (c2 >= nws) mbar_wait(BAR(7 + s2), ((c2 / nws) - 1) & 1);
           mbar_arrive_expect_tx(BAR(4 + s2), w_chunk_bytes);
-          bulk_g2s(smem_u32(w_buf + s2 * kWStageBytes), wsrc + (size_t)c2 * w_chunk_bytes,
+          bulk_g2s(smem_u32(w_buf + s2 * wsb), wsrc + (size_t)c2 * w_chunk_bytes,
                    w_chunk_bytes, BAR(4 + s2));
         }
-        const int ws = kc % kWStages, ab = kc & 1;
-        mbar_wait(BAR(4 + ws), (kc / kWStages) & 1);
+        const int ws = kc % nws, ab = kc & 1;
+        mbar_wait(BAR(4 + ws), (kc / nws) & 1);
         mbar_wait(BAR(0 + ab), (kc >> 1) & 1);
         tc_fence_after_sync();
         int ksteps = (a.K - kc * kKC + 15) / 16;
         if (ksteps > 4) ksteps = 4;
         const uint32_t a_addr = smem_u32(a_buf + ab * kABufBytes);
-        const uint32_t w_addr = smem_u32(w_buf + ws * kWStageBytes);
+        const uint32_t w_addr = smem_u32(w_buf + ws * wsb);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           for (int ks = 0; ks < ksteps; ++ks) {
@@ -278,7 +285,7 @@ int launch_linear_tc(const LinArgs& f, const void* packed_w, cudaStream_t st) {
                                   kSmemBytes));
     attr_set = true;
   }
-  linear_tc_kernel<<<cdiv(f.M, 256), 288, kSmemBytes, st>>>(a);
+  linear_tc_kernel<<<cdiv(f.M, 256), 288, smem_bytes(a.Npad), st>>>(a);
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }

@@ -524,6 +524,11 @@ struct Prod {
   // in[(row / bdiv) * ldin + c], optionally scaled per row
   int grad_w(const float* dz, long long lddz, int out, long long rows, const float* in, long long ldin, int width,
              float* dW, long long ldw, long long bdiv = 1, const float* kscale = nullptr) const {
+    if (tc && bdiv == 1 && width > 256 && tc_grad_w_ok(out, 256, rows)) {  // 257 = 256 + 1: two passes over dz
+      int rc = tc_grad_w(dz, lddz, out, rows, in, ldin, 256, kscale, dW, ldw, st);
+      if (rc) return rc;
+      return grad_w(dz, lddz, out, rows, in + 256, ldin, width - 256, dW + 256, ldw, 1, kscale);
+    }
     if (tc && bdiv == 1 && tc_grad_w_ok(out, width, rows))
       return tc_grad_w(dz, lddz, out, rows, in, ldin, width, kscale, dW, ldw, st);
     GemmArgs g{dz, in, dW, out, width, rows, 1, lddz, ldin, 1, ldw, 1, 0};
@@ -534,6 +539,11 @@ struct Prod {
   // din[rows, width] (+)= dz[rows, out] W[out, coloff : coloff + width]   (W row-major with ldw columns)
   int grad_in(const float* dz, long long lddz, int out, long long rows, const float* W, long long ldw, int width,
               float* din, long long ldd, bool accumulate = false) const {
+    if (tc && !accumulate && width > 256 && tc_grad_in_ok(out, 256, rows)) {
+      int rc = tc_grad_in(dz, lddz, out, rows, W, ldw, 256, din, ldd, img, st);
+      if (rc) return rc;
+      return grad_in(dz, lddz, out, rows, W + 256, ldw, width - 256, din + 256, ldd, false);
+    }
     if (tc && !accumulate && tc_grad_in_ok(out, width, rows))
       return tc_grad_in(dz, lddz, out, rows, W, ldw, width, din, ldd, img, st);
     GemmArgs g{dz, W, din, rows, width, out, lddz, 1, ldw, 1, ldd, accumulate ? 1 : 0, 0};
@@ -728,7 +738,9 @@ int net_dynamic_backward(const dyn_net* n, const float* pts, const float* rgb_fe
   TR(pr.dense(L.rgb2, q.p64, P, d.ch2, d.ch, q.pX, true));
   TR(pr.elu(q.pX, 128, d.ch, 128, 128, P));
   TR(pr.grad_w(q.pX, 128, 128, P, d.G4, 128, 128, dprm + L.rgb0.w, 155));
-  TR(pr.grad_w(q.pX, 128, 128, P, d.dirpe, 27, 27, dprm + L.rgb0.w + 128, 155, S));
+  // the direction encoding is per ray: sum dz over the samples of a ray first, then a product over R rows
+  TR(pr.gsum(q.pX, 128, 128, R, S, q.rA, 128));
+  TR(pr.grad_w(q.rA, 128, 128, R, d.dirpe, 27, 27, dprm + L.rgb0.w + 128, 155));
   TR(pr.bias(q.pX, 128, 128, P, L.rgb0.b));
   TR(pr.grad_in(q.pX, 128, 128, P, prm + L.rgb0.w, 155, 128, q.pA, 128));  // q.pA = dG4
   TR(pr.grad_w(q.pS, 1, 1, P, d.sh, 128, 128, dprm + L.outgeo2.w, 128));

@@ -24,9 +24,10 @@ using namespace tc;
 namespace {
 
 constexpr int kRowsStage = 64;                       // K per stage
-constexpr int kOpBytes = 256 * kRowsStage * 2;       // one operand image of a stage (up to 256 columns): 32 KB
-constexpr int kStageBytes = 2 * kOpBytes;            // A + B
-constexpr int kGwSmem = 2 * kStageBytes + 1024;
+// one stage = A image (Mpad columns) + B image (Npad columns) of 64 rows; two stages.  256 x 256: 128 KB (one CTA
+// per SM); 128 x 128: 64 KB (three per SM)
+__host__ __device__ constexpr int gw_stage_bytes(int Mpad, int Npad) { return (Mpad + Npad) * kRowsStage * 2; }
+__host__ __device__ constexpr int gw_smem(int Mpad, int Npad) { return 2 * gw_stage_bytes(Mpad, Npad) + 1024; }
 
 struct GradWArgs {
   const float* dz; long long lddz; int out;
@@ -63,8 +64,10 @@ __device__ __forceinline__ uint4 load8_bf16(const float* __restrict__ p, long lo
   return q;
 }
 
-__global__ void __launch_bounds__(288, 1) grad_w_tc_kernel(const __grid_constant__ GradWArgs a) {
+__global__ void __launch_bounds__(288, 2) grad_w_tc_kernel(const __grid_constant__ GradWArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const int kStageBytes = gw_stage_bytes(a.Mpad, a.Npad);
+  const int kOpBytes = a.Mpad * kRowsStage * 2;  // the A image; the B image follows it
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes);
   // bars: [0,1] full (256 arrivals), [2,3] empty (tcgen05.commit), [4] done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
@@ -114,8 +117,10 @@ __global__ void __launch_bounds__(288, 1) grad_w_tc_kernel(const __grid_constant
       mma_commit(BAR(4));
     }
   } else {
-    // ---------------- loaders: thread -> (row of the stage, column-group phase) ----------------
-    const int srow = tid & 63, gsel = tid >> 6;  // 4 column groups per pass
+    // ---------------- loaders: four lanes read 4 x 32 B = one 128-byte line of a row (8 lines per warp
+    //                  instruction instead of 32); a warp owns 8 rows of the stage ----------------
+    const int lane = tid & 31;
+    const int srow = warp * 8 + (lane >> 2), gsel = lane & 3;  // row of the stage, chunk phase
     const bool dz_vec = (a.lddz & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dz) & 15) == 0;
     const bool x_vec = (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
     const int ga = a.Mpad >> 3, gb = a.Npad >> 3;
@@ -128,12 +133,25 @@ __global__ void __launch_bounds__(288, 1) grad_w_tc_kernel(const __grid_constant
       if (s >= 2) mbar_wait(BAR(2 + sb), ((s >> 1) - 1) & 1);
       uint8_t* abase = smem + sb * kStageBytes + srow * 16;
       uint8_t* bbase = abase + kOpBytes;
-      for (int g = gsel; g < ga; g += 4)
-        *reinterpret_cast<uint4*>(abase + g * (kRowsStage * 16)) =
-            load8_bf16(a.dz, a.lddz, row, rows_lim, g * 8, a.out, 1.f, dz_vec);
-      for (int g = gsel; g < gb; g += 4)
-        *reinterpret_cast<uint4*>(bbase + g * (kRowsStage * 16)) =
-            load8_bf16(a.x, a.ldx, row, rows_lim, g * 8, a.width, sc, x_vec);
+      // batches of four 16-byte chunks: all loads of a batch are in flight before the first store
+      for (int g0 = gsel; g0 < ga; g0 += 16) {
+        uint4 q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (g0 + 4 * j < ga) q[j] = load8_bf16(a.dz, a.lddz, row, rows_lim, (g0 + 4 * j) * 8, a.out, 1.f, dz_vec);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (g0 + 4 * j < ga) *reinterpret_cast<uint4*>(abase + (g0 + 4 * j) * (kRowsStage * 16)) = q[j];
+      }
+      for (int g0 = gsel; g0 < gb; g0 += 16) {
+        uint4 q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (g0 + 4 * j < gb) q[j] = load8_bf16(a.x, a.ldx, row, rows_lim, (g0 + 4 * j) * 8, a.width, sc, x_vec);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (g0 + 4 * j < gb) *reinterpret_cast<uint4*>(bbase + (g0 + 4 * j) * (kRowsStage * 16)) = q[j];
+      }
       fence_proxy_async_smem();
       mbar_arrive(BAR(0 + sb));
     }
@@ -182,7 +200,7 @@ __global__ void pack_wt_tc_kernel(const float* __restrict__ W, long long ldw, in
 
 }  // namespace
 
-bool tc_grad_w_ok(int out, int width, long long rows) { return out >= 8 && out <= 256 && width >= 8 && width <= 256 && rows >= 2048; }
+bool tc_grad_w_ok(int out, int width, long long rows) { return out >= 1 && out <= 256 && width >= 1 && width <= 256 && rows >= 2048; }
 bool tc_grad_in_ok(int out, int width, long long rows) { return width >= 16 && width <= 256 && out >= 16 && rows >= 2048; }
 size_t tc_grad_in_scratch_bytes() { return tc_packed_bytes(256, 320); }
 
@@ -195,18 +213,26 @@ int tc_grad_w(const float* dz, long long lddz, int out, long long rows, const fl
   a.rows = rows; a.dW = dW; a.ldw = ldw;
   a.Mpad = out <= 128 ? 128 : 256;
   a.Npad = (width + 15) / 16 * 16;
-  // slabs: enough CTAs to fill the GPU a few times over, at least 1024 rows each (the atomics of the epilogue are
-  // out x width per CTA)
-  long long per = (rows + 591) / 592;
+  // slabs: one wave of CTAs (as many as fit the GPU at this tile size), at least 1024 rows each: the epilogue adds
+  // out x width floats per CTA with atomics
+  const int smem = gw_smem(a.Mpad, a.Npad);
+  int per_sm = (227 * 1024) / smem;
+  const int tm = (a.Mpad / 128) * a.Npad;  // TMEM columns (allocated as a power of two >= 32)
+  int tcols = 32;
+  while (tcols < tm) tcols *= 2;
+  if (per_sm > 512 / tcols) per_sm = 512 / tcols;
+  if (per_sm > 2) per_sm = 2;  // launch bounds
+  if (per_sm < 1) per_sm = 1;
+  long long per = (rows + 148LL * per_sm - 1) / (148LL * per_sm);
   per = per < 1024 ? 1024 : per;
   per = (per + kRowsStage - 1) / kRowsStage * kRowsStage;
   a.rows_per_cta = per;
   static bool attr_set = false;
   if (!attr_set) {
-    DYN_CUDA(cudaFuncSetAttribute(grad_w_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGwSmem));
+    DYN_CUDA(cudaFuncSetAttribute(grad_w_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gw_smem(256, 256)));
     attr_set = true;
   }
-  grad_w_tc_kernel<<<(unsigned)((rows + per - 1) / per), 288, kGwSmem, st>>>(a);
+  grad_w_tc_kernel<<<(unsigned)((rows + per - 1) / per), 288, smem, st>>>(a);
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }
