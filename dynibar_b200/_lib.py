@@ -94,6 +94,10 @@ SIGNATURES = {
     "dyn_encoder_param_count": (_sz, []),
     "dyn_encoder_workspace_bytes": (_sz, [_i, _i, _i]),
     "dyn_encoder_forward": (_i, [_vp, _sz, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "dyn_encoder_train_workspace_bytes": (_sz, [_i, _i, _i]),
+    "dyn_encoder_backward_scratch_bytes": (_sz, [_i, _i, _i]),
+    "dyn_encoder_train_forward": (_i, [_vp, _sz, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "dyn_encoder_backward": (_i, [_vp, _sz, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _i, _vp]),
     "dyn_flow_sceneflow": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i,
                                 _vp, _vp, _vp]),
 }

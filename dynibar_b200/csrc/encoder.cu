@@ -10,6 +10,7 @@
 // fp32 SIMT kernels with register tiling (a few ms per frame against > 400 ms of ray rendering; bf16
 // tensor-core convolutions would buy < 1 % of the frame).  All statistics in fp64 accumulators.
 #include "common.cuh"
+#include "train_gemm.cuh"
 
 namespace dyn {
 
@@ -236,6 +237,184 @@ int in_norm(const float* x, const float* P, int gw, int gb, const float* residua
   return DYN_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// training (row f2): backward of the executed encoder.  Every convolution is differentiated through its im2col
+// form so that the two products run on the shared training GEMMs (tensor cores in bf16 mode):
+//   dYt [rows, 64]       = dY (NCHW) with rows = (n, oy, ox)
+//   col [rows, Cin k k]  = im2col(X) with the forward's reflect padding / stride, column = ci k k + ky k + kx
+//                          (the layout of conv.weight [co][ci][ky][kx], so dW = dYt^T col is the weight gradient as is)
+//   dcol = dYt W  ->  col2im: scatter-add through the SAME index map (the adjoint of reflect padding for free)
+// ---------------------------------------------------------------------------
+__global__ void enc_nchw_to_rows_kernel(const float* __restrict__ x, int C, int hw, long long rows,
+                                        float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * C) return;
+  const long long r = idx / C;
+  const int c = (int)(idx - r * C);
+  const long long n = r / hw, pix = r - n * hw;
+  out[idx] = x[(n * C + c) * hw + pix];
+}
+
+// mode 0: col[r, j] = X[...];  mode 1: atomicAdd(dX[...], col[r, j])
+__global__ void enc_im2col_kernel(float* __restrict__ x, int Cin, int H, int W, int Ho, int Wo, int k, int stride,
+                                  int pad, long long rows, float* __restrict__ col, int mode) {
+  const int K = Cin * k * k;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * K) return;
+  const long long r = idx / K;
+  const int j = (int)(idx - r * K);
+  const int ci = j / (k * k), t = j - ci * k * k, ky = t / k, kx = t - ky * k;
+  const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho);
+  const long long n = r / ((long long)Wo * Ho);
+  const int iy = reflect_idx(oy * stride + ky - pad, H), ix = reflect_idx(ox * stride + kx - pad, W);
+  float* p = x + ((n * Cin + ci) * H + iy) * W + ix;
+  if (mode == 0) col[idx] = *p;
+  else atomicAdd(p, col[idx]);
+}
+
+__global__ void enc_relu_mask_kernel(float* __restrict__ g, const float* __restrict__ y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(y[i] > 0.f)) g[i] = 0.f;
+}
+
+__global__ void enc_add_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
+}
+
+// InstanceNorm2d backward, one block per (image, channel) plane: xh = (x - mean) rstd,
+// dx = rstd gamma (dy - mean(dy) - xh mean(dy xh)); dgamma += sum dy xh, dbeta += sum dy.  dx may alias dy.
+__global__ void __launch_bounds__(256) enc_in_bwd_kernel(const float* __restrict__ x, const float* dy,
+                                                         const float* __restrict__ mean,
+                                                         const float* __restrict__ rstd,
+                                                         const float* __restrict__ gamma, int hw, int C, float* dx,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const long long plane = blockIdx.x;
+  const int c = (int)(plane % C);
+  const float* xp = x + plane * hw;
+  const float* gp = dy + plane * hw;
+  const float m = mean[plane], rs = rstd[plane];
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < hw; i += 256) {
+    const double g = gp[i];
+    s1 += g;
+    s2 += g * (double)((xp[i] - m) * rs);
+  }
+  __shared__ double a1[256], a2[256];
+  a1[threadIdx.x] = s1; a2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { a1[threadIdx.x] += a1[threadIdx.x + o]; a2[threadIdx.x] += a2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const float mg = (float)(a1[0] / hw), mgx = (float)(a2[0] / hw);
+  const float k = rs * gamma[c];
+  float* op = dx + plane * hw;
+  for (int i = threadIdx.x; i < hw; i += 256) {
+    const float xh = (xp[i] - m) * rs;
+    op[i] = k * (gp[i] - mg - xh * mgx);
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(dgamma + c, (float)a2[0]);
+    atomicAdd(dbeta + c, (float)a1[0]);
+  }
+}
+
+// saved activations of the training forward (floats)
+struct EncSaved {
+  float *c1, *a1;                         // half resolution: conv1 output, relu(IN(.))
+  struct B { float *cA, *aA, *cB, *o; } b[3];
+  float* cds;                             // block 0 shortcut conv output (before its InstanceNorm)
+  float* stats[8];                        // mean | rstd per InstanceNorm: bn1, b0.bn1, b0.bn2, b0.ds, b1.bn1, b1.bn2, b2.*
+};
+
+size_t enc_saved_alloc(char* base, int N, int H2, int W2, int H4, int W4, EncSaved* s) {
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += n * sizeof(float);
+    return p;
+  };
+  const size_t n2 = (size_t)N * 64 * H2 * W2, n4 = (size_t)N * 64 * H4 * W4;
+  s->c1 = take(n2); s->a1 = take(n2);
+  for (int i = 0; i < 3; ++i) { s->b[i].cA = take(n4); s->b[i].aA = take(n4); s->b[i].cB = take(n4); s->b[i].o = take(n4); }
+  s->cds = take(n4);
+  for (int i = 0; i < 8; ++i) s->stats[i] = take((size_t)2 * N * 64);
+  return off;
+}
+
+struct EncScratch {
+  float *g2a, *g2b;        // half-resolution gradients
+  float *g4a, *g4b, *g4c;  // quarter-resolution gradients
+  float *dyt, *col, *img;
+};
+
+size_t enc_scratch_alloc(char* base, int N, int H, int W, int H2, int W2, int H4, int W4, EncScratch* q) {
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += n * sizeof(float);
+    return p;
+  };
+  (void)H; (void)W;
+  const size_t n2 = (size_t)N * 64 * H2 * W2, n4 = (size_t)N * 64 * H4 * W4;
+  const size_t r2 = (size_t)N * H2 * W2, r4 = (size_t)N * H4 * W4;
+  q->g2a = take(n2); q->g2b = take(n2);
+  q->g4a = take(n4); q->g4b = take(n4); q->g4c = take(n4);
+  q->dyt = take(r2 * 64 > r4 * 64 ? r2 * 64 : r4 * 64);
+  const size_t c_stem = r2 * 147, c_33 = r4 * 576;
+  q->col = take(c_stem > c_33 ? c_stem : c_33);
+  q->img = take(tc_grad_in_scratch_bytes() / sizeof(float));
+  return off;
+}
+
+// backward of one convolution (see the header of this section).  dX: null = not needed; acc_dx: add to dX
+struct ConvBwd {
+  cudaStream_t st;
+  bool tc;
+  EncScratch q;
+  int N;
+  int run(const float* dY, int Ho, int Wo, const float* Wt, float* dW, float* X, int Cin, int H, int W, int k,
+          int stride, int pad, float* dX, bool zero_dx) const {
+    const long long rows = (long long)N * Ho * Wo;
+    const int K = Cin * k * k;
+    enc_nchw_to_rows_kernel<<<cdiv(rows * 64, 256), 256, 0, st>>>(dY, 64, Ho * Wo, rows, q.dyt);
+    DYN_LAUNCH_CHECK();
+    enc_im2col_kernel<<<cdiv(rows * K, 256), 256, 0, st>>>(X, Cin, H, W, Ho, Wo, k, stride, pad, rows, q.col, 0);
+    DYN_LAUNCH_CHECK();
+    for (int c0 = 0; c0 < K; c0 += 256) {  // dW[64, K] += dYt^T col
+      const int wd = K - c0 < 256 ? K - c0 : 256;
+      int rc;
+      if (tc && tc_grad_w_ok(64, wd, rows)) {
+        rc = tc_grad_w(q.dyt, 64, 64, rows, q.col + c0, K, wd, nullptr, dW + c0, K, st);
+      } else {
+        GemmArgs g{q.dyt, q.col + c0, dW + c0, 64, wd, rows, 1, 64, K, 1, K, 1, 0};
+        rc = launch_gemm(g, true, st);
+      }
+      if (rc) return rc;
+    }
+    if (dX == nullptr) return DYN_OK;
+    for (int c0 = 0; c0 < K; c0 += 256) {  // dcol[rows, K] = dYt W  (overwrites col)
+      const int wd = K - c0 < 256 ? K - c0 : 256;
+      int rc;
+      if (tc && tc_grad_in_ok(64, wd, rows)) {
+        rc = tc_grad_in(q.dyt, 64, 64, rows, Wt + c0, K, wd, q.col + c0, K, q.img, st);
+      } else {
+        GemmArgs g{q.dyt, Wt + c0, q.col + c0, rows, wd, 64, 64, 1, K, 1, K, 0, 0};
+        rc = launch_gemm(g, false, st);
+      }
+      if (rc) return rc;
+    }
+    if (zero_dx) DYN_CUDA(cudaMemsetAsync(dX, 0, (size_t)N * Cin * H * W * sizeof(float), st));
+    enc_im2col_kernel<<<cdiv(rows * K, 256), 256, 0, st>>>(dX, Cin, H, W, Ho, Wo, k, stride, pad, rows, q.col, 1);
+    DYN_LAUNCH_CHECK();
+    return DYN_OK;
+  }
+};
+
 }  // namespace
 }  // namespace dyn
 
@@ -306,6 +485,153 @@ int dyn_encoder_forward(const float* params, size_t n_params, const float* image
   DYN_CUDA(cudaMemcpy2DAsync(fine, 32 * plane, reinterpret_cast<char*>(b3) + 32 * plane, 64 * plane, 32 * plane, N,
                              cudaMemcpyDeviceToDevice, st));
   return DYN_OK;
+}
+
+// ---- training (row f2) -------------------------------------------------------------------------
+static void enc_dims(int H, int W, int* H2, int* W2, int* H4, int* W4) {
+  *H2 = (H + 6 - 7) / 2 + 1; *W2 = (W + 6 - 7) / 2 + 1;
+  *H4 = (*H2 + 2 - 3) / 2 + 1; *W4 = (*W2 + 2 - 3) / 2 + 1;
+}
+
+size_t dyn_encoder_train_workspace_bytes(int N, int H, int W) {
+  int H2, W2, H4, W4;
+  enc_dims(H, W, &H2, &W2, &H4, &W4);
+  EncSaved s;
+  return enc_saved_alloc(nullptr, N, H2, W2, H4, W4, &s) + (size_t)N * 64 * H4 * W4 * sizeof(float) + 256;
+}
+
+size_t dyn_encoder_backward_scratch_bytes(int N, int H, int W) {
+  int H2, W2, H4, W4;
+  enc_dims(H, W, &H2, &W2, &H4, &W4);
+  EncScratch q;
+  return enc_scratch_alloc(nullptr, N, H, W, H2, W2, H4, W4, &q);
+}
+
+int dyn_encoder_train_forward(const float* params, size_t n_params, const float* images, int N, int H, int W,
+                              float* coarse, float* fine, void* saved, size_t saved_bytes, void* stream) {
+  const EncLayout L = enc_layout();
+  DYN_CHECK_ARG(params && images && coarse && fine && saved && N >= 1 && H >= 8 && W >= 8);
+  if (n_params != (size_t)L.total)
+    return fail(DYN_E_INVALID, "encoder: got %zu parameters, expected %d", n_params, L.total);
+  if (saved_bytes < dyn_encoder_train_workspace_bytes(N, H, W))
+    return fail(DYN_E_WORKSPACE, "encoder: saved workspace %zu < %zu", saved_bytes, dyn_encoder_train_workspace_bytes(N, H, W));
+  cudaStream_t st = (cudaStream_t)stream;
+  int H2, W2, H4, W4;
+  enc_dims(H, W, &H2, &W2, &H4, &W4);
+  EncSaved s;
+  const size_t used = enc_saved_alloc((char*)saved, N, H2, W2, H4, W4, &s);
+  float* outb = reinterpret_cast<float*>((char*)saved + ((used + 255) & ~(size_t)255));  // out_conv result [N,64,h,w]
+  const float* P = params;
+  int rc;
+  enc_conv7_kernel<<<dim3(cdiv(W2, 16), cdiv(H2, 8), N), 128, 0, st>>>(images, P + L.conv1, H, W, H2, W2, s.c1);
+  DYN_LAUNCH_CHECK();
+  if ((rc = in_norm(s.c1, P, L.bn1w, L.bn1b, nullptr, 1, N, H2 * W2, s.stats[0], s.a1, st))) return rc;
+  const dim3 g4(cdiv(W4, 16), cdiv(H4, 8), N);
+  const float* xin = s.a1;
+  for (int b = 0; b < 3; ++b) {
+    if (b == 0) enc_conv3_kernel<2><<<g4, 128, 0, st>>>(xin, P + L.blk[0].c1, H2, W2, H4, W4, s.b[0].cA);
+    else enc_conv3_kernel<1><<<g4, 128, 0, st>>>(xin, P + L.blk[b].c1, H4, W4, H4, W4, s.b[b].cA);
+    DYN_LAUNCH_CHECK();
+    if ((rc = in_norm(s.b[b].cA, P, L.blk[b].b1w, L.blk[b].b1b, nullptr, 1, N, H4 * W4,
+                      s.stats[b == 0 ? 1 : 2 * b + 2], s.b[b].aA, st))) return rc;
+    enc_conv3_kernel<1><<<g4, 128, 0, st>>>(s.b[b].aA, P + L.blk[b].c2, H4, W4, H4, W4, s.b[b].cB);
+    DYN_LAUNCH_CHECK();
+    const float* resid = xin;
+    if (b == 0) {
+      enc_conv1_kernel<2><<<cdiv((long long)N * H4 * W4 * 4, 256), 256, 0, st>>>(s.a1, P + L.blk[0].dsw, nullptr, H2, W2,
+                                                                                   H4, W4, N, s.cds);
+      DYN_LAUNCH_CHECK();
+      // the normalised shortcut lives in block 0's output buffer until the sum replaces it
+      if ((rc = in_norm(s.cds, P, L.blk[0].dsbw, L.blk[0].dsbb, nullptr, 0, N, H4 * W4, s.stats[3], s.b[0].o, st))) return rc;
+      resid = s.b[0].o;
+    }
+    if ((rc = in_norm(s.b[b].cB, P, L.blk[b].b2w, L.blk[b].b2b, resid, 1, N, H4 * W4,
+                      s.stats[b == 0 ? 2 : 2 * b + 3], s.b[b].o, st))) return rc;
+    xin = s.b[b].o;
+  }
+  enc_conv1_kernel<1><<<cdiv((long long)N * H4 * W4 * 4, 256), 256, 0, st>>>(xin, P + L.outw, P + L.outb, H4, W4, H4, W4,
+                                                                               N, outb);
+  DYN_LAUNCH_CHECK();
+  const size_t plane = (size_t)H4 * W4 * sizeof(float);
+  DYN_CUDA(cudaMemcpy2DAsync(coarse, 32 * plane, outb, 64 * plane, 32 * plane, N, cudaMemcpyDeviceToDevice, st));
+  DYN_CUDA(cudaMemcpy2DAsync(fine, 32 * plane, reinterpret_cast<char*>(outb) + 32 * plane, 64 * plane, 32 * plane, N,
+                             cudaMemcpyDeviceToDevice, st));
+  return DYN_OK;
+}
+
+int dyn_encoder_backward(const float* params, size_t n_params, const float* images, int N, int H, int W,
+                         const float* d_coarse, const float* d_fine, void* saved, size_t saved_bytes, void* scratch,
+                         size_t scratch_bytes, float* d_params, int precision, void* stream) {
+  const EncLayout L = enc_layout();
+  DYN_CHECK_ARG(params && images && saved && scratch && d_params && (d_coarse || d_fine) && N >= 1);
+  DYN_CHECK_ARG(precision == DYN_PREC_FP32 || precision == DYN_PREC_BF16);
+  if (n_params != (size_t)L.total)
+    return fail(DYN_E_INVALID, "encoder: got %zu parameters, expected %d", n_params, L.total);
+  if (saved_bytes < dyn_encoder_train_workspace_bytes(N, H, W) || scratch_bytes < dyn_encoder_backward_scratch_bytes(N, H, W))
+    return fail(DYN_E_WORKSPACE, "encoder backward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int H2, W2, H4, W4;
+  enc_dims(H, W, &H2, &W2, &H4, &W4);
+  EncSaved s;
+  enc_saved_alloc((char*)saved, N, H2, W2, H4, W4, &s);
+  EncScratch q;
+  enc_scratch_alloc((char*)scratch, N, H, W, H2, W2, H4, W4, &q);
+  const float* P = params;
+  float* dP = d_params;
+  const int hw4 = H4 * W4, hw2 = H2 * W2;
+  const long long n4 = (long long)N * 64 * hw4, n2 = (long long)N * 64 * hw2;
+  const size_t plane = (size_t)hw4 * sizeof(float);
+  const ConvBwd cb{st, precision == DYN_PREC_BF16, q, N};
+  int rc;
+  auto in_bwd = [&](const float* x, float* g, const float* stats, int gw, int gb, int hw) {
+    enc_in_bwd_kernel<<<N * 64, 256, 0, st>>>(x, g, stats, stats + N * 64, P + gw, hw, 64, g, dP + gw, dP + gb);
+    DYN_LAUNCH_CHECK();
+    return DYN_OK;
+  };
+  auto relu_mask = [&](float* g, const float* y, long long n) {
+    enc_relu_mask_kernel<<<cdiv(n, 256), 256, 0, st>>>(g, y, n);
+    DYN_LAUNCH_CHECK();
+    return DYN_OK;
+  };
+  // d(out_conv output) [N,64,h,w] = [d_coarse | d_fine]
+  float* g = q.g4a;
+  DYN_CUDA(cudaMemsetAsync(g, 0, (size_t)n4 * sizeof(float), st));
+  if (d_coarse) DYN_CUDA(cudaMemcpy2DAsync(g, 64 * plane, d_coarse, 32 * plane, 32 * plane, N, cudaMemcpyDeviceToDevice, st));
+  if (d_fine) DYN_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(g) + 32 * plane, 64 * plane, d_fine, 32 * plane, 32 * plane, N,
+                                         cudaMemcpyDeviceToDevice, st));
+  // out_conv (1x1, bias): db = sum over pixels; dW, d(o2)
+  float* d_o = q.g4b;
+  if ((rc = cb.run(g, H4, W4, P + L.outw, dP + L.outw, s.b[2].o, 64, H4, W4, 1, 1, 0, d_o, true))) return rc;
+  if ((rc = launch_colsum(q.dyt, 64, 64, (long long)N * hw4, dP + L.outb, st))) return rc;  // q.dyt = rows of g
+  // blocks 2, 1 (identity shortcuts), then block 0
+  float* t = q.g4a;   // free again
+  float* u = q.g4c;
+  for (int b = 2; b >= 1; --b) {
+    float* xin = s.b[b - 1].o;
+    if ((rc = relu_mask(d_o, s.b[b].o, n4))) return rc;                       // d_sum in d_o
+    DYN_CUDA(cudaMemcpyAsync(t, d_o, (size_t)n4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if ((rc = in_bwd(s.b[b].cB, t, s.stats[2 * b + 3], L.blk[b].b2w, L.blk[b].b2b, hw4))) return rc;   // d cB
+    if ((rc = cb.run(t, H4, W4, P + L.blk[b].c2, dP + L.blk[b].c2, s.b[b].aA, 64, H4, W4, 3, 1, 1, u, true))) return rc;
+    if ((rc = relu_mask(u, s.b[b].aA, n4))) return rc;
+    if ((rc = in_bwd(s.b[b].cA, u, s.stats[2 * b + 2], L.blk[b].b1w, L.blk[b].b1b, hw4))) return rc;   // d cA
+    // d xin = d_sum (identity shortcut, already in d_o) + conv1 backward, accumulated in place
+    if ((rc = cb.run(u, H4, W4, P + L.blk[b].c1, dP + L.blk[b].c1, xin, 64, H4, W4, 3, 1, 1, d_o, false))) return rc;
+  }
+  // block 0: stride 2, shortcut = IN(conv1x1 stride 2)
+  if ((rc = relu_mask(d_o, s.b[0].o, n4))) return rc;
+  DYN_CUDA(cudaMemcpyAsync(t, d_o, (size_t)n4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if ((rc = in_bwd(s.b[0].cB, t, s.stats[2], L.blk[0].b2w, L.blk[0].b2b, hw4))) return rc;
+  if ((rc = cb.run(t, H4, W4, P + L.blk[0].c2, dP + L.blk[0].c2, s.b[0].aA, 64, H4, W4, 3, 1, 1, u, true))) return rc;
+  if ((rc = relu_mask(u, s.b[0].aA, n4))) return rc;
+  if ((rc = in_bwd(s.b[0].cA, u, s.stats[1], L.blk[0].b1w, L.blk[0].b1b, hw4))) return rc;
+  float* d_a1 = q.g2a;
+  if ((rc = cb.run(u, H4, W4, P + L.blk[0].c1, dP + L.blk[0].c1, s.a1, 64, H2, W2, 3, 2, 1, d_a1, true))) return rc;
+  if ((rc = in_bwd(s.cds, d_o, s.stats[3], L.blk[0].dsbw, L.blk[0].dsbb, hw4))) return rc;           // d cds (in d_o)
+  if ((rc = cb.run(d_o, H4, W4, P + L.blk[0].dsw, dP + L.blk[0].dsw, s.a1, 64, H2, W2, 1, 2, 0, d_a1, false))) return rc;
+  // stem: relu, InstanceNorm, conv1 (only its weight gradient: the images carry none)
+  if ((rc = relu_mask(d_a1, s.a1, n2))) return rc;
+  if ((rc = in_bwd(s.c1, d_a1, s.stats[0], L.bn1w, L.bn1b, hw2))) return rc;
+  return cb.run(d_a1, H2, W2, P + L.conv1, dP + L.conv1, const_cast<float*>(images), 3, H, W, 7, 2, 3, nullptr, false);
 }
 
 }  // extern "C"

@@ -4,7 +4,9 @@ The container reproduces the reference module tree (same constructor, same `stat
 the layer2 / layer3 / decoder parameters the reference builds but never runs, feature_network.py:302-311 --
 so published checkpoints load strictly).  `forward` runs the executed part on the CUDA library
 (csrc/encoder.cu: conv7x7 s2 -> InstanceNorm -> ReLU -> 3 BasicBlocks -> 1x1 conv) and returns
-(coarse [N,32,H/4,W/4], fine [N,32,H/4,W/4]) like the reference.  No PyTorch math here.
+(coarse [N,32,H/4,W/4], fine [N,32,H/4,W/4]) like the reference.  No PyTorch math here.  With gradients enabled and
+parameters that require grad the forward keeps its activations and `backward()` runs the library's encoder backward
+(`torch.autograd.Function` below): the gradients of the executed parameters, as train.py's optimiser expects.
 """
 
 import torch
@@ -102,8 +104,12 @@ class ResNet(nn.Module):
     """x [N,3,H,W] in [0,1] -> (coarse [N,32,h,w], fine [N,32,h,w]), h = H/4, w = W/4."""
     if self.coarse_out_ch != 32 or self.fine_out_ch != 32:
       raise NotImplementedError("the CUDA encoder is built for coarse_out_ch = fine_out_ch = 32")
-    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-      raise NotImplementedError("dynibar_b200 kernels are forward-only (SURVEY 8(f) f2)")
+    if torch.is_grad_enabled() and any(self.state_dict(keep_vars=True)[k].requires_grad for k in _EXECUTED):
+      if x.requires_grad:
+        raise NotImplementedError("the encoder backward does not produce a gradient of the input images")
+      from dynibar_b200.autograd import _prec_code
+      sd = self.state_dict(keep_vars=True)
+      return _EncoderFn.apply(x, _prec_code(None), *[sd[k] for k in _EXECUTED])
     dev = dev_of(x)
     xi = f32c(x)
     N, _, H, W = xi.shape
@@ -118,3 +124,51 @@ class ResNet(nn.Module):
       check(lib.dyn_encoder_forward(ptr(blob), blob.numel(), ptr(xi), N, H, W, ptr(coarse), ptr(fine),
                                     ws.data_ptr(), nbytes, stream()))
     return coarse, fine
+
+
+class _EncoderFn(torch.autograd.Function):
+  """ResNet.forward (executed part) with its backward kernels (csrc/encoder.cu, training section)."""
+
+  @staticmethod
+  def forward(ctx, x, prec, *params):
+    dev = dev_of(x)
+    xi = f32c(x)
+    N, _, H, W = xi.shape
+    H2, W2 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    h, w = (H2 + 2 - 3) // 2 + 1, (W2 + 2 - 3) // 2 + 1
+    blob = torch.cat([p.detach().reshape(-1).float() for p in params]).to(dev).contiguous()
+    coarse = torch.empty(N, 32, h, w, device=dev)
+    fine = torch.empty(N, 32, h, w, device=dev)
+    nbytes = int(lib.dyn_encoder_train_workspace_bytes(N, H, W))
+    saved = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+      check(lib.dyn_encoder_train_forward(ptr(blob), blob.numel(), ptr(xi), N, H, W, ptr(coarse), ptr(fine),
+                                          saved.data_ptr(), nbytes, stream()))
+    ctx.blob, ctx.x, ctx.saved, ctx.nbytes, ctx.prec = blob, xi, saved, nbytes, prec
+    ctx.shapes = [p.shape for p in params]
+    return coarse, fine
+
+  @staticmethod
+  def backward(ctx, g_coarse, g_fine):
+    xi = ctx.x
+    N, _, H, W = xi.shape
+    dev = xi.device
+    gc = f32c(g_coarse) if g_coarse is not None else None
+    gf = f32c(g_fine) if g_fine is not None else None
+    d_params = torch.zeros_like(ctx.blob)
+    sbytes = int(lib.dyn_encoder_backward_scratch_bytes(N, H, W))
+    scratch = _lib.workspace.get(sbytes, dev, slot=3)
+    with torch.cuda.device(dev):
+      check(lib.dyn_encoder_backward(ptr(ctx.blob), ctx.blob.numel(), ptr(xi), N, H, W,
+                                     ptr(gc) if gc is not None else None, ptr(gf) if gf is not None else None,
+                                     ctx.saved.data_ptr(), ctx.nbytes, scratch.data_ptr(), sbytes, ptr(d_params),
+                                     ctx.prec, stream()))
+    ctx.saved = None
+    grads, o = [], 0
+    for shp in ctx.shapes:
+      n = 1
+      for d in shp:
+        n *= d
+      grads.append(d_params[o:o + n].reshape(shp))
+      o += n
+    return (None, None) + tuple(grads)

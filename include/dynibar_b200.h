@@ -233,6 +233,20 @@ int dyn_resample(const float* z_vals, const float* weights, const float* u,
                  int R, int S, int Ni, int inv_uniform, float* z_out,
                  void* stream);
 
+/* Training of the 2-D encoder (row f2; autograd of ResNet.forward, feature_network.py:302-311 with BasicBlock.forward
+ * :68-84).  The train forward keeps every pre-norm convolution output, activation and InstanceNorm statistic in `saved`
+ * (dyn_encoder_train_workspace_bytes); the backward ACCUMULATES d(loss)/d(params) into d_params (n_params floats, the
+ * order of dyn_encoder_forward's `params`; the caller zeroes it) from d_coarse / d_fine [N,32,H/4,W/4] (either may be
+ * NULL).  The images carry no gradient.  Every convolution is differentiated through its im2col form; `precision`
+ * DYN_PREC_BF16 runs the two products per convolution on tcgen05 (bf16 operands, fp32 accumulation). */
+size_t dyn_encoder_train_workspace_bytes(int N, int H, int W);
+size_t dyn_encoder_backward_scratch_bytes(int N, int H, int W);
+int dyn_encoder_train_forward(const float* params, size_t n_params, const float* images, int N, int H, int W,
+                              float* coarse, float* fine, void* saved, size_t saved_bytes, void* stream);
+int dyn_encoder_backward(const float* params, size_t n_params, const float* images, int N, int H, int W,
+                         const float* d_coarse, const float* d_fine, void* saved, size_t saved_bytes,
+                         void* scratch, size_t scratch_bytes, float* d_params, int precision, void* stream);
+
 /* ---- a14: flow / expected scene flow, render_ray.py:333-358, :585-595 -----
  * weights [R,S]; pts_seq [V,R,S,3] (first n_flow views used); src_cams
  * [V,34]; uv [R,2]; coeff [R,S,3*nb]; basis [T,nb]; sf_k = 2 (mv) or 1 (mono).

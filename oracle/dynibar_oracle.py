@@ -696,6 +696,40 @@ def _cross_time(ray_batch, feat_anchor, pts, z, aux, frame_idx, time_embedding, 
 
 
 # -----------------------------------------------------------------------------
+# f1 2-D encoder  (ibrnet/feature_network.py:302-311 with BasicBlock.forward :68-84)
+# -----------------------------------------------------------------------------
+def _conv_reflect(x, w, stride, pad, bias=None):
+  """nn.Conv2d(padding_mode='reflect') (feature_network.py:16-38, :224-232)."""
+  if pad:
+    x = F.pad(x, (pad, pad, pad, pad), mode="reflect")
+  return F.conv2d(x, w, bias, stride=stride)
+
+
+def _inst_norm(x, w, b):
+  """nn.InstanceNorm2d(track_running_stats=False, affine=True), eps 1e-5 (:60-64)."""
+  return F.instance_norm(x, weight=w, bias=b, eps=1e-5)
+
+
+def encoder_forward(w, x):
+  """The executed part of ResNet.forward (feature_network.py:302-311): `w` = state_dict (or a dict of leaf
+  tensors), x [N,3,H,W] -> (coarse [N,32,H/4,W/4], fine [N,32,H/4,W/4])."""
+  w = _sd(w)
+  x = torch.relu(_inst_norm(_conv_reflect(x, w["conv1.weight"], 2, 3), w["bn1.weight"], w["bn1.bias"]))
+  for b in range(3):
+    p = "layer1.%d." % b
+    ident = x
+    out = _conv_reflect(x, w[p + "conv1.weight"], 2 if b == 0 else 1, 1)
+    out = torch.relu(_inst_norm(out, w[p + "bn1.weight"], w[p + "bn1.bias"]))
+    out = _inst_norm(_conv_reflect(out, w[p + "conv2.weight"], 1, 1), w[p + "bn2.weight"], w[p + "bn2.bias"])
+    if b == 0:  # downsample = conv1x1 stride 2 + InstanceNorm (:243-252)
+      ident = _inst_norm(_conv_reflect(x, w[p + "downsample.0.weight"], 2, 0), w[p + "downsample.1.weight"],
+                         w[p + "downsample.1.bias"])
+    x = torch.relu(out + ident)
+  out = _conv_reflect(x, w["out_conv.weight"], 1, 0, w["out_conv.bias"])
+  return out[:, :32], out[:, -32:]
+
+
+# -----------------------------------------------------------------------------
 # parity metric (eval_nvidia.py:201-225, full-image branch)
 # -----------------------------------------------------------------------------
 def psnr(a, b):

@@ -62,3 +62,35 @@ def test_encoder_feeds_the_renderer_layout():
   m = _model(1).to(DEV)
   c, f = m(torch.rand(8, 3, 288, 512, device=DEV))
   assert c.shape == (8, 32, 72, 128) and f.shape == (8, 32, 72, 128) and torch.isfinite(c).all()
+
+
+@pytest.mark.parametrize("N,H,W,prec", [(2, 60, 84, "fp32"), (3, 37, 53, "fp32"), (2, 192, 256, "bf16")])
+def test_encoder_backward_matches_oracle_autograd(N, H, W, prec):
+  """Row f2: gradients of every executed encoder parameter against torch autograd through the oracle's restatement of
+  ResNet.forward (pinned to the reference by tests/test_oracle_golden.py).  fp32: 2e-3 relative L2 per tensor
+  (InstanceNorm + ReLU network; the ReLU kinks make a few units flip with the summation order); bf16 products
+  (tcgen05): 1e-1."""
+  from dynibar_b200 import render_ray as rr
+  from oracle import dynibar_oracle as orc
+  m = _model(N * 100 + H).requires_grad_(True)
+  g = torch.Generator().manual_seed(N + H)
+  x = torch.rand(N, 3, H, W, generator=g)
+  w = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items() if k in fn._EXECUTED}
+  wc, wf = orc.encoder_forward(w, x)
+  gc, gf = torch.randn(wc.shape, generator=g), torch.randn(wf.shape, generator=g)
+  ((wc * gc).sum() + (wf * gf).sum()).backward()
+  md = m.to(DEV)
+  with rr.precision_scope(prec):
+    c, f = md(x.to(DEV))
+    assert c.requires_grad and f.requires_grad
+    ((c * gc.to(DEV)).sum() + (f * gf.to(DEV)).sum()).backward()
+  torch.testing.assert_close(c.detach().cpu(), wc.detach(), rtol=2e-4, atol=2e-4)
+  tol = 2e-3 if prec == "fp32" else 1e-1
+  sd = md.state_dict(keep_vars=True)
+  for k in fn._EXECUTED:
+    assert sd[k].grad is not None, k
+    d = (sd[k].grad.cpu().double() - w[k].grad.double()).norm().item()
+    assert d <= tol * w[k].grad.double().norm().item() + 1e-6, (k, d, w[k].grad.norm().item())
+  for k, p in md.named_parameters():  # parameters the reference builds but never runs get no gradient
+    if k not in fn._EXECUTED:
+      assert p.grad is None, k

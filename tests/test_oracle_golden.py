@@ -146,3 +146,24 @@ def test_oracle_matches_live_reference():
   for k in ("outputs_coarse_ref", "outputs_fine_ref", "outputs_fine_ref_dy"):
     for kk in want[k]:
       _cmp("%s/%s" % (k, kk), got[k][kk], want[k][kk])
+
+
+def test_oracle_encoder_matches_reference_fixture(golden):
+  """oracle.encoder_forward (feature_network.py:302-311) against outputs of the unmodified reference ResNet
+  (tests/golden/encoder.pt); it is the autograd reference of the encoder's backward kernels."""
+  from dynibar_b200 import feature_network as fn
+  fx = golden("encoder")
+  torch.manual_seed(fx["seed"])
+  m = fn.ResNet()
+  with torch.no_grad():  # same initialisation as tests/test_encoder_gpu.py::_model
+    for name, p in m.named_parameters():
+      if name.endswith("bn1.weight") or name.endswith("bn2.weight") or name.endswith("downsample.1.weight"):
+        p.uniform_(0.5, 1.5)
+      elif name.endswith(".bias"):
+        p.uniform_(-0.3, 0.3)
+  g = torch.Generator().manual_seed(fx["seed"] + 1)
+  x = torch.rand(*fx["shape"], generator=g)
+  with torch.no_grad():
+    c, f = orc.encoder_forward(m, x)
+  torch.testing.assert_close(c, fx["coarse"], rtol=2e-4, atol=2e-4)
+  torch.testing.assert_close(f, fx["fine"], rtol=2e-4, atol=2e-4)
