@@ -18,6 +18,7 @@ from dynibar_b200._lib import lib  # noqa: E402
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 rays = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
+with_encoder = len(sys.argv) > 4 and sys.argv[4] == "encoder"  # feature maps = ResNet(source images), trained too
 dev = torch.device("cuda:0")
 batch, feat_c, _, frame, t, offs = synthetic.make_scene(H=288, W=512, V_dy=8, V_st=8, num_vv=2, seed=3, rays=rays,
                                                         anchor_offset=2)
@@ -29,16 +30,29 @@ params = []
 for m in mods:
   m.requires_grad_(True)
   params += list(m.parameters())
-feat = tuple(f.to(dev).requires_grad_(True) for f in feat_c)
-opt = torch.optim.Adam(params + list(feat), lr=1e-4)
 b = synthetic.to_device(batch, dev)
+if with_encoder:
+  from dynibar_b200 import feature_network
+  torch.manual_seed(5)
+  enc = feature_network.ResNet().to(dev)
+  enc.requires_grad_(True)
+  imgs = [b[k][0].permute(0, 3, 1, 2).contiguous() for k in ("src_rgbs", "anchor_src_rgbs", "static_src_rgbs")]
+  opt = torch.optim.Adam(params + list(enc.parameters()), lr=1e-4)
+else:
+  feat = tuple(f.to(dev).requires_grad_(True) for f in feat_c)
+  opt = torch.optim.Adam(params + list(feat), lr=1e-4)
 target = torch.rand(rays, 3, device=dev)
 proj = Projector(dev)
 
 
 def step():
   opt.zero_grad(set_to_none=True)
-  ret = rr.render_rays_mono(frame, t, offs, b, model, feat, proj, 64, args, inv_uniform=True, det=False, is_train=True,
+  if with_encoder:  # train.py:264-281: coarse feature maps of the reference / anchor / static source views
+    with rr.precision_scope(prec):
+      fm = tuple(enc(im)[0] for im in imgs)
+  else:
+    fm = feat
+  ret = rr.render_rays_mono(frame, t, offs, b, model, fm, proj, 64, args, inv_uniform=True, det=False, is_train=True,
                             num_vv=2, precision=prec)
   loss = ((ret["outputs_coarse_ref"]["rgb"] - target) ** 2).mean()
   loss = loss + ((ret["outputs_coarse_anchor"]["rgb"] - target) ** 2).mean()
@@ -61,7 +75,7 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(json.dumps({"what": "training step, BASELINE config 3 shape (render_rays_mono is_train=True, fwd + bwd + Adam)",
-                  "rays": rays, "samples": 64, "views": "6+2 dynamic, 8 static, 6+2 anchor", "precision": prec,
+                  "rays": rays, "samples": 64, "views": "6+2 dynamic, 8 static, 6+2 anchor", "precision": prec, "encoder_in_step": with_encoder,
                   "ms_per_step": ms, "rays_per_s": rays / ms * 1e3, "loss_first": float(l0), "loss_last": float(l1),
                   "kernel_launches_per_step": (lib.dyn_launch_count(0) - n0) / steps,
                   "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
