@@ -174,6 +174,59 @@ def make_cpu_runner():
   return "port", run
 
 
+def train_step_line(dev, precision, rays=1024, steps=3):
+  """Secondary line: BASELINE configs[2] -- one training step of N_rand = 1024 rays x 64 samples through the
+  differentiable render_rays_mono (cross-time branch included), 2-D encoder forward + backward over the 24 source
+  images, Adam step; synthetic 512x288 scene.  Loss terms are a stand-in (two photometric + flow + scene-flow)."""
+  from dynibar_b200 import feature_network, render_ray as rr, synthetic
+  from dynibar_b200.projection import Projector
+  batch, _, _, frame, t, offs = synthetic.make_scene(H=288, W=512, V_dy=8, V_st=8, num_vv=2, seed=3, rays=rays,
+                                                     anchor_offset=2)
+  args = synthetic.make_args(1, 1, 0)
+  model, args = synthetic.make_model(64, 0, args=args, seed=3, mono=True)
+  model = synthetic.model_to(model, dev)
+  params = []
+  for m in (model.net_coarse_dy, model.net_coarse_st, model.motion_mlp):
+    m.requires_grad_(True)
+    params += list(m.parameters())
+  torch.manual_seed(5)
+  enc = feature_network.ResNet().to(dev).requires_grad_(True)
+  b = synthetic.to_device(batch, dev)
+  imgs = [b[k][0].permute(0, 3, 1, 2).contiguous() for k in ("src_rgbs", "anchor_src_rgbs", "static_src_rgbs")]
+  opt = torch.optim.Adam(params + list(enc.parameters()), lr=1e-4)
+  target = torch.rand(rays, 3, device=dev)
+  proj = Projector(dev)
+
+  def step():
+    opt.zero_grad(set_to_none=True)
+    with rr.precision_scope(precision):
+      fm = tuple(enc(im)[0] for im in imgs)  # train.py:264-281
+      ret = rr.render_rays_mono(frame, t, offs, b, model, fm, proj, 64, args, inv_uniform=True, det=False,
+                                is_train=True, num_vv=2)
+    loss = ((ret["outputs_coarse_ref"]["rgb"] - target) ** 2).mean()
+    loss = loss + ((ret["outputs_coarse_anchor"]["rgb"] - target) ** 2).mean()
+    loss = loss + 1e-3 * ret["outputs_coarse_ref"]["render_flows"].abs().mean()
+    loss = loss + 1e-2 * ret["outputs_coarse_anchor"]["sf_seq"].abs().mean()
+    loss.backward()
+    opt.step()
+    return loss
+
+  for _ in range(2):
+    l0 = step()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(steps):
+    l1 = step()
+  e1.record()
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / steps
+  return {"what": "BASELINE configs[2] shape: training step (encoder + render_rays_mono is_train=True, forward + "
+                  "backward + Adam), N_rand %d, 64 samples, 6+2 / 8 / 6+2 views" % rays,
+          "precision": precision, "ms_per_step": ms, "value": rays / ms * 1e3, "unit": "rays/s",
+          "loss_first": float(l0), "loss_last": float(l1)}
+
+
 def main():
   a = parse()
   rank = int(os.environ.get("RANK", "0"))
@@ -375,6 +428,9 @@ def main():
                             "ms_per_step": ms_e / 2, "flop_per_ray": fpr_e,
                             "tflops": a.rays * 2 / (ms_e / 1e3) * fpr_e / 1e12}
     del fe
+
+  if not a.no_extras and world == 1:
+    extras["train_step"] = train_step_line(dev, a.precision)
 
   total_rays = fr.n_total * a.steps
   value = total_rays / (ms / 1e3)
