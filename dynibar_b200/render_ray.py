@@ -605,8 +605,8 @@ def render_rays_mono(frame_idx, time_embedding, time_offset, ray_batch, model, f
   the forward-only kernels (fused tcgen05 path in bf16 mode) under no_grad."""
   if _wants_grad(model, featmaps):
     with precision_scope(precision):
-      return _render_mono_train(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, N_samples,
-                                args, inv_uniform, det, is_train, num_vv, jitter)
+      return _render_mono_train_chunked(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps,
+                                        N_samples, args, inv_uniform, det, is_train, num_vv, jitter)
   with torch.no_grad(), precision_scope(precision):
     t = _scalar(time_embedding[0].float())
     ray_batch, hb = _with_host_copies(ray_batch, model, ("trajectory_basis",))
@@ -674,6 +674,42 @@ def _cross_time(ray_batch, feat_anchor, pts, z, aux, ref_idx, anc_idx, t_anc, an
 # ---------------------------------------------------------------------------
 # f2: differentiable render_rays_mono (training step)
 # ---------------------------------------------------------------------------
+# (point, view) rows one training call of a network may hold (csrc/nets_f32.cu: net_rows_per_chunk; the training
+# forward keeps every activation of ONE internal chunk); larger ray batches are rendered in slices
+TRAIN_ROWS_LIMIT = 4194304
+_RAY_AXIS1 = ("render_flows", "pts_traj_ref", "pts_traj_anchor", "sf_seq")  # [n, R, ...]; every other key is [R, ...]
+
+
+def _render_mono_train_chunked(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, N_samples, args,
+                               inv_uniform, det, is_train, num_vv, jitter):
+  """Slices the rays so that no network call exceeds TRAIN_ROWS_LIMIT rows and concatenates the per-slice output
+  dicts along their ray axis (autograd sees one graph; gradients accumulate over the slices)."""
+  R = ray_batch["ray_o"].shape[0]
+  vmax = max(ray_batch[k].shape[1] for k in ("src_cameras", "static_src_cameras", "anchor_src_cameras")
+             if k in ray_batch and (is_train or k != "anchor_src_cameras"))
+  per = max(1, TRAIN_ROWS_LIMIT // (N_samples * vmax))
+  if R <= per:
+    return _render_mono_train(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, N_samples, args,
+                              inv_uniform, det, is_train, num_vv, jitter)
+  parts = []
+  for lo in range(0, R, per):
+    hi = min(R, lo + per)
+    rb = dict(ray_batch)
+    for k in ("ray_o", "ray_d", "uv_grid"):
+      rb[k] = ray_batch[k][lo:hi]
+    parts.append(_render_mono_train(frame_idx, time_embedding, time_offset, rb, model, featmaps, N_samples, args,
+                                    inv_uniform, det, is_train, num_vv,
+                                    None if jitter is None else jitter[lo:hi]))
+  ret = {}
+  for name, first in parts[0].items():
+    if first is None:
+      ret[name] = None
+      continue
+    ret[name] = OrderedDict((k, torch.cat([p[name][k] for p in parts], 1 if k in _RAY_AXIS1 else 0))
+                            for k in first)
+  return ret
+
+
 def _render_mono_train(frame_idx, time_embedding, time_offset, ray_batch, model, featmaps, N_samples, args,
                        inv_uniform, det, is_train, num_vv, jitter):
   """render_rays_mono (render_ray.py:870-1277) with autograd: the same sequence as the reference, every stage a

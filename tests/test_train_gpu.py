@@ -315,3 +315,40 @@ def test_tensorcore_training_products(rows, out, width, ldx_pad, scaled):
     assert (din[:, width] == 7.0).all()
     err = (din[:, :width].cpu().double() - want_in).norm() / want_in.norm()
     assert err < 2e-5, ("grad_in", err.item())
+
+
+def test_training_ray_slices_match_one_call(monkeypatch):
+  """Ray batches whose (point, view) rows exceed one internal chunk are rendered in slices: same outputs, same
+  gradients (accumulated over the slices by autograd) as the single call."""
+  from dynibar_b200 import render_ray as rr
+  from dynibar_b200.projection import Projector
+  cfg = dict(scenes.GOLDEN_CONFIGS["mono_train"])
+  batch, feat_c, _, frame, t, offs, model, args = scenes.build(cfg)
+  dev = torch.device(DEV)
+  m_dev = synthetic.model_to(model, dev)
+  mods = (m_dev.net_coarse_dy, m_dev.net_coarse_st, m_dev.motion_mlp)
+  for mod in mods:
+    mod.requires_grad_(True)
+  b = synthetic.to_device(batch, dev)
+  g = torch.Generator().manual_seed(4)
+  results = []
+  for limit in (rr.TRAIN_ROWS_LIMIT, 7 * cfg["N_samples"] * 8):  # the second forces slices of 7 rays
+    monkeypatch.setattr(rr, "TRAIN_ROWS_LIMIT", limit)
+    for mod in mods:
+      mod.zero_grad(set_to_none=True)
+    fd = tuple(f.to(dev).requires_grad_(True) for f in feat_c)
+    got = rr.render_rays_mono(frame, t, offs, b, m_dev, fd, Projector(dev), cfg["N_samples"], args,
+                              inv_uniform=True, det=True, is_train=True, num_vv=cfg["num_vv"], precision="fp32")
+    if not results:
+      gens = {(o, k): torch.randn(got[o][k].shape, generator=g).to(dev) for o, ks in _TRAIN_KEYS.items() for k in ks}
+    sum((got[o][k] * v).sum() for (o, k), v in gens.items()).backward()
+    # (`s`: ill-conditioned sum, see above -- its value depends on the summation order)
+    results.append((got, [p.grad.clone() for mod in mods for k, p in mod.named_parameters() if k != "s"],
+                    [f.grad.clone() for f in fd]))
+  (a, ga, fa), (bb, gb, fb) = results
+  for o, ks in _TRAIN_KEYS.items():
+    for k in ks:
+      torch.testing.assert_close(bb[o][k], a[o][k], rtol=1e-5, atol=1e-6, msg=lambda s: "%s/%s: %s" % (o, k, s))
+  assert torch.equal(bb["outputs_coarse_ref"]["mask"], a["outputs_coarse_ref"]["mask"])
+  for x, y in zip(gb + fb, ga + fa):
+    assert (x - y).norm().item() <= 2e-3 * y.norm().item() + 1e-6
