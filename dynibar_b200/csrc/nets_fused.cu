@@ -19,11 +19,11 @@ constexpr int kDefaultViewKernel = 2;  // sub-round pipelined twin kernel (profi
 // kernel with sub-round pipelined layers (view_twin3.cu).  DYN_VIEW_KERNEL=twin|quad|pipe or
 // dyn_debug_set_view_kernel(); profiles/r02_view_kernels.md has the comparison.
 static int g_view_kernel = -1;
-void set_view_kernel(int which) { g_view_kernel = (which >= 0 && which <= 2) ? which : -1; }
+void set_view_kernel(int which) { g_view_kernel = (which >= 0 && which <= 3) ? which : -1; }
 static int view_kernel() {
   if (g_view_kernel < 0) {
     const char* e = getenv("DYN_VIEW_KERNEL");
-    g_view_kernel = e == nullptr ? kDefaultViewKernel : (e[0] == 'q' ? 1 : (e[0] == 'p' ? 2 : 0));
+    g_view_kernel = e == nullptr ? kDefaultViewKernel : (e[0] == 'q' ? 1 : (e[0] == 'p' ? 2 : (e[0] == 'e' ? 3 : 0)));
   }
   return g_view_kernel;
 }
@@ -66,7 +66,8 @@ int launch_view_fused(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
   }
   switch (view_kernel()) {
     case 1: return launch_view_quad(n, a, V, st);
-    case 2: return launch_view_twin3(n, a, V, st);
+    case 2: return launch_view_twin3(n, a, V, st, false);
+    case 3: return launch_view_twin3(n, a, V, st, true);  // + one barrier arrival per warp ("elected")
     default: return launch_view_twin(n, a, V, st);
   }
 }

@@ -146,7 +146,7 @@ int launch_view_twin(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st)
 // sub-round pipelined twin-warp per-view stage (view_twin3.cu)
 size_t view_twin3_bytes(int kind);
 int view_twin3_build(dyn_net* n, const float* host_params, void* dst_dev, size_t dst_bytes, cudaStream_t st);
-int launch_view_twin3(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st);
+int launch_view_twin3(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st, bool elected_arrive = false);
 
 // quad-schedule per-view stage (view_quad.cu): one CTA per SM, two tiles, four threads per row
 size_t view_quad_bytes(int kind);

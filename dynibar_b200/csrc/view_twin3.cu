@@ -107,7 +107,10 @@ __device__ __forceinline__ void elu_block_to_A(uint8_t* arow, uint32_t tacc, int
   }
 }
 
-template <int VP, bool ST, int NT>
+// EA ("elected arrive"): the operand barriers count WARPS, not threads: every thread fences its own writes
+// (fence.proxy.async + tcgen05.fence::before_thread_sync), the warp converges (__syncwarp orders the lanes' memory
+// operations) and lane 0 arrives once -- 32 same-address shared-memory atomics per warp instruction become one
+template <int VP, bool ST, int NT, bool EA>
 __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
     view_twin3_kernel(const __grid_constant__ ViewFusedArgs a) {
   constexpr int ROWS = 128 * NT;          // rows per iteration
@@ -127,7 +130,8 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
   if (tid == 0) {
     init_barriers(bar0, PP, /*arrivals=*/NT == 2 ? 256 : 128, RING);
     if (NT == 1) {  // second operand barrier (sub-round 1 of the pipelined layers): both twins arrive once
-      mbar_init(bar_aready(bar0, 1, RING), 256);
+      mbar_init(bar_aready(bar0, 1, RING), EA ? 8 : 256);
+      if (EA) mbar_init(bar_aready(bar0, 0, RING), 8);
       mbar_fence_init();
     }
   }
@@ -167,6 +171,15 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
     issuer_loop<PP, NT, RING, kTwinStage>(s_tab, a.nchunks, n_iter, smem, ring, bar0, tmem_base, kTwinATile,
                            a.dbg ? a.dbg + 128 : nullptr);
   } else {
+#define ARRIVE(bar)                                   \
+  do {                                                \
+    if (EA) {                                         \
+      __syncwarp();                                   \
+      if ((tid & 31) == 0) mbar_arrive(bar);          \
+    } else {                                          \
+      mbar_arrive(bar);                               \
+    }                                                 \
+  } while (0)
     const int tw = tid / ROWS;         // twin index
     const int t = tid % ROWS;          // row slot inside the iteration
     const int tile = t >> 7, r = t & 127;
@@ -324,7 +337,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(bar_aready(bar0, bt, RING));
+        ARRIVE(bar_aready(bar0, bt, RING));
       }
 
       TS();  // 1: after F1 operand + arrive
@@ -384,7 +397,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         elu_log2_block_to_A<128>(arow, tacc, 128 * tw);
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(bar_aready(bar0, bt, RING));
+        ARRIVE(bar_aready(bar0, bt, RING));
         TS();  // 4: F1 epilogue done
         // ---- F2: src_feat (35 of 48 columns) * ref_feat; twin 0 keeps 0..17, twin 1 keeps 18..34.
         //      The per-ray reference feature is loaded BEFORE the wait (its L2 latency hides behind the MMA) ----
@@ -457,7 +470,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           if (ST && g == 2) {
             fence_proxy_async_smem();
             tc_fence_before_sync();
-            mbar_arrive(bar_aready(bar0, bt, RING));
+            ARRIVE(bar_aready(bar0, bt, RING));
           }
         }
         {  // zero the K padding (static: 120..127 / 248..255, dynamic: 120..127)
@@ -468,7 +481,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_aready(bar0, ST ? 1 : 0, RING));  // static: sub-round 1 of base_fc.0 (second operand barrier)
+      ARRIVE(bar_aready(bar0, ST ? 1 : 0, RING));  // static: sub-round 1 of base_fc.0 (second operand barrier)
 
       TS();  // 6: pool1 done + arrive
       // From here on every layer runs in TWO sub-rounds: the twins own interleaved 32-column blocks, arrive after
@@ -487,7 +500,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         if (j & 1) {
           fence_proxy_async_smem();
           tc_fence_before_sync();
-          mbar_arrive(bar_aready(bar0, j >> 1, RING));  // first / second operand barrier
+          ARRIVE(bar_aready(bar0, j >> 1, RING));  // first / second operand barrier
         }
       }
 
@@ -510,7 +523,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(bar_aready(bar0, j, RING));
+        ARRIVE(bar_aready(bar0, j, RING));
       }
 
       TS();  // 10: F4 epilogue done
@@ -536,7 +549,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           if (j == 1) xch5[tw * 128 + t] = part;
           fence_proxy_async_smem();
           tc_fence_before_sync();
-          mbar_arrive(bar_aready(bar0, j, RING));
+          ARRIVE(bar_aready(bar0, j, RING));
         }
       }
 
@@ -571,10 +584,11 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
           }
           pk[i] = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        if (ST && !(a.ablate & 2)) {
-          // spilled as a bf16 tile image (fused_engine.cuh) in view-slot row order: the blending head lands it
-          // in its operand tile with one bulk copy per 128 rows
-          uint8_t* xo = reinterpret_cast<uint8_t*>(a.X) + tile_image_off((long long)it * ROWS + t, cb >> 3, 16);
+        // spilled as a bf16 tile image (fused_engine.cuh) in view-slot row order: the blending head lands it
+        // in its operand tile with one bulk copy per 128 rows.  EA: the global stores are issued AFTER the operand
+        // barrier arrival (fence.proxy.async is a MEMBAR: it would wait for them to be performed first)
+        uint8_t* xo = reinterpret_cast<uint8_t*>(a.X) + tile_image_off((long long)it * ROWS + t, cb >> 3, 16);
+        if (!EA && ST && !(a.ablate & 2)) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(xo + i * 2048) = pk[i];
         }
@@ -582,7 +596,11 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(arow + ((cb >> 3) + i) * 2048) = pk[i];
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(bar_aready(bar0, j, RING));
+        ARRIVE(bar_aready(bar0, j, RING));
+        if (EA && ST && !(a.ablate & 2)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(xo + i * 2048) = pk[i];
+        }
       }
 
       TS();  // 14: F6 epilogue done
@@ -691,6 +709,7 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       tc_fence_before_sync();
     }
 #undef TS
+#undef ARRIVE
   }
   __syncthreads();
   if (warp == W_ISSUE) {
@@ -812,7 +831,7 @@ int view_twin3_build(dyn_net* n, const float* P, void* dst_dev, size_t dst_bytes
   return DYN_OK;
 }
 
-int launch_view_twin3(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st) {
+int launch_view_twin3(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st, bool elected_arrive) {
   if (n->twin3.img == nullptr) return fail(DYN_E_INVALID, "net has no twin-warp view images");
   a.wimg = n->twin3.img;
   a.chunks = n->twin3.tab;
@@ -825,7 +844,8 @@ int launch_view_twin3(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
     DYN_CUDA(cudaGetDevice(&dev));
     DYN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 #define PREP_VT(VPV, STV) \
-    DYN_CUDA(cudaFuncSetAttribute(view_twin3_kernel<VPV, STV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, twin_smem(1)))
+    DYN_CUDA(cudaFuncSetAttribute(view_twin3_kernel<VPV, STV, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, twin_smem(1))); \
+    DYN_CUDA(cudaFuncSetAttribute(view_twin3_kernel<VPV, STV, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, twin_smem(1)))
     PREP_VT(8, true); PREP_VT(16, true); PREP_VT(8, false); PREP_VT(16, false);
 #undef PREP_VT
     ablate = e ? atoi(e) : 0;
@@ -838,13 +858,19 @@ int launch_view_twin3(const dyn_net* n, ViewFusedArgs& a, int V, cudaStream_t st
   if (grid == 0) return DYN_OK;
   const bool st_net = n->kind == DYN_NET_STATIC;
   ProfScope prof(st_net ? PROF_VIEW_ST : PROF_VIEW_DY, st);
+#define LAUNCH_VT3(VPV, STV)                                                                     \
+  do {                                                                                          \
+    if (elected_arrive) view_twin3_kernel<VPV, STV, 1, true><<<grid, 320, twin_smem(1), st>>>(a);  \
+    else view_twin3_kernel<VPV, STV, 1, false><<<grid, 320, twin_smem(1), st>>>(a);               \
+  } while (0)
   if (st_net) {
-    if (VP == 8) view_twin3_kernel<8, true, 1><<<grid, 320, twin_smem(1), st>>>(a);
-    else view_twin3_kernel<16, true, 1><<<grid, 320, twin_smem(1), st>>>(a);
+    if (VP == 8) LAUNCH_VT3(8, true);
+    else LAUNCH_VT3(16, true);
   } else {
-    if (VP == 8) view_twin3_kernel<8, false, 1><<<grid, 320, twin_smem(1), st>>>(a);
-    else view_twin3_kernel<16, false, 1><<<grid, 320, twin_smem(1), st>>>(a);
+    if (VP == 8) LAUNCH_VT3(8, false);
+    else LAUNCH_VT3(16, false);
   }
+#undef LAUNCH_VT3
   DYN_LAUNCH_CHECK();
   return DYN_OK;
 }
