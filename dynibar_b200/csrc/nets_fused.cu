@@ -12,7 +12,7 @@
 
 namespace dyn {
 
-constexpr int kDefaultViewKernel = 2;  // sub-round pipelined twin kernel (profiles/r02_kernels.md)
+constexpr int kDefaultViewKernel = 3;  // sub-round pipelined twin kernel + software-pipelined TMEM read-out (profiles/r02_kernels.md)
 
 // Three schedules of the same per-tile work: 0 = the twin-warp kernel (view_twin.cu: two independent CTAs per
 // SM), 1 = the quad kernel (view_quad.cu: one CTA per SM alternating between two tiles), 2 = the twin-warp

@@ -107,6 +107,31 @@ __device__ __forceinline__ void elu_block_to_A(uint8_t* arow, uint32_t tacc, int
   }
 }
 
+// tcgen05.wait::ld that carries a data dependency on the 16 destination registers of the load it waits for (so no
+// use of them can be scheduled above it)
+__device__ __forceinline__ void tmem_wait_ld_dep16(float* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
+
+// Software-pipelined accumulator read-out: NH half-blocks of 16 TMEM columns; the load of half h + 1 is in flight
+// while fn(h, values) processes half h (TMEM reads run at 64 B/clk: a 32-column load of one warp occupies the port
+// for 64 cycles, and eight row warps per CTA queue on it).  colf(h) = TMEM column of half h.
+template <int NH, class ColFn, class Fn>
+__device__ __forceinline__ void tmem_pipe16(uint32_t tacc, ColFn colf, Fn fn) {
+  float buf[2][16];
+  tmem_ld16(tacc + colf(0), buf[0]);
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    tmem_wait_ld_dep16(buf[h & 1]);
+    if (h + 1 < NH) tmem_ld16(tacc + colf(h + 1), buf[(h + 1) & 1]);
+    fn(h, buf[h & 1]);
+  }
+}
+
 // EA ("elected arrive"): the operand barriers count WARPS, not threads: every thread fences its own writes
 // (fence.proxy.async + tcgen05.fence::before_thread_sync), the warp converges (__syncwarp orders the lanes' memory
 // operations) and lane 0 arrives once -- 32 same-address shared-memory atomics per warp instruction become one
@@ -394,7 +419,16 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
         TS();  // 3: F1 acc ready
         tc_fence_after_sync();
-        elu_log2_block_to_A<128>(arow, tacc, 128 * tw);
+        if (EA) {
+          tmem_pipe16<8>(tacc, [&](int h) { return 128 * tw + 16 * h; }, [&](int h, float* v) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = elu_log2(v[i]);
+            store8(arow, 128 * tw + 16 * h, v);
+            store8(arow, 128 * tw + 16 * h + 8, v + 8);
+          });
+        } else {
+          elu_log2_block_to_A<128>(arow, tacc, 128 * tw);
+        }
         fence_proxy_async_smem();
         tc_fence_before_sync();
         ARRIVE(bar_aready(bar0, bt, RING));
@@ -493,14 +527,29 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
       TS();  // 7: F3 acc ready
       tc_fence_after_sync();
+      if (EA) {
+        auto col3 = [&](int h) { const int j = h >> 1; return 32 * ((j < 2 ? 4 : 0) + 2 * (j & 1) + tw) + 16 * (h & 1); };
+        tmem_pipe16<8>(tacc, col3, [&](int h, float* v) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = elu_log2(v[i]);
+          store8(arow, col3(h), v);
+          store8(arow, col3(h) + 8, v + 8);
+          if ((h & 3) == 3) {
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            ARRIVE(bar_aready(bar0, h >> 2, RING));  // first / second operand barrier
+          }
+        });
+      } else {
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int col = 32 * ((j < 2 ? 4 : 0) + 2 * (j & 1) + tw);
-        elu_log2_block_to_A<32>(arow, tacc, col);
-        if (j & 1) {
-          fence_proxy_async_smem();
-          tc_fence_before_sync();
-          ARRIVE(bar_aready(bar0, j >> 1, RING));  // first / second operand barrier
+        for (int j = 0; j < 4; ++j) {
+          const int col = 32 * ((j < 2 ? 4 : 0) + 2 * (j & 1) + tw);
+          elu_log2_block_to_A<32>(arow, tacc, col);
+          if (j & 1) {
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            ARRIVE(bar_aready(bar0, j >> 1, RING));  // first / second operand barrier
+          }
         }
       }
 
@@ -511,19 +560,34 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       mbar_wait(bar_acc(bar0, bt, RING), acc_cnt & 1); ++acc_cnt;
       TS();  // 9: F4 acc ready
       tc_fence_after_sync();
+      auto colh = [&](int h) { return 32 * (2 * (h >> 1) + tw) + 16 * (h & 1); };  // this twin's blocks tw, 2 + tw
+      if (EA) {
+        tmem_pipe16<4>(tacc + 128, colh, [&](int h, float* v) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = elu_from_log2(v[i]);
+          store8(arow, colh(h), v);
+          store8(arow, colh(h) + 8, v + 8);
+          if (h & 1) {
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            ARRIVE(bar_aready(bar0, h >> 1, RING));
+          }
+        });
+      } else {
 #pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
-        const int cb = 32 * (2 * j + tw);
-        float acc[32];
-        tmem_ld32(tacc + 128 + cb, acc);
-        tmem_wait_ld();
+        for (int j = 0; j < 2; ++j) {
+          const int cb = 32 * (2 * j + tw);
+          float acc[32];
+          tmem_ld32(tacc + 128 + cb, acc);
+          tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = elu_from_log2(acc[i]);
+          for (int i = 0; i < 32; ++i) acc[i] = elu_from_log2(acc[i]);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        ARRIVE(bar_aready(bar0, j, RING));
+          for (int g = 0; g < 4; ++g) store8(arow, cb + 8 * g, acc + 8 * g);
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          ARRIVE(bar_aready(bar0, j, RING));
+        }
       }
 
       TS();  // 10: F4 epilogue done
@@ -533,23 +597,42 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       tc_fence_after_sync();
       {
         float part = 0.f;
+        if (EA) {
+          tmem_pipe16<4>(tacc, colh, [&](int h, float* v) {
+            const int c0 = colh(h);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[i] = elu_log2(fmaf(v[i], w1, cst[T_B5 + c0 + i]));  // log2(e) * ELU(w1 (W x) + b)
+              part = fmaf(v[i], cst[T_W6V + c0 + i], part);
+            }
+            store8(arow, 128 + c0, v);
+            store8(arow, 128 + c0 + 8, v + 8);
+            if (h & 1) {
+              if (h == 3) xch5[tw * 128 + t] = part;
+              fence_proxy_async_smem();
+              tc_fence_before_sync();
+              ARRIVE(bar_aready(bar0, h >> 1, RING));
+            }
+          });
+        } else {
 #pragma unroll 1
-        for (int j = 0; j < 2; ++j) {
-          const int cb = 32 * (2 * j + tw);
-          float acc[32];
-          tmem_ld32(tacc + cb, acc);
-          tmem_wait_ld();
+          for (int j = 0; j < 2; ++j) {
+            const int cb = 32 * (2 * j + tw);
+            float acc[32];
+            tmem_ld32(tacc + cb, acc);
+            tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            acc[i] = elu_log2(fmaf(acc[i], w1, cst[T_B5 + cb + i]));  // log2(e) * ELU(w1 (W x) + b)
-            part = fmaf(acc[i], cst[T_W6V + cb + i], part);
+            for (int i = 0; i < 32; ++i) {
+              acc[i] = elu_log2(fmaf(acc[i], w1, cst[T_B5 + cb + i]));  // log2(e) * ELU(w1 (W x) + b)
+              part = fmaf(acc[i], cst[T_W6V + cb + i], part);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) store8(arow, 128 + cb + 8 * g, acc + 8 * g);
+            if (j == 1) xch5[tw * 128 + t] = part;
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            ARRIVE(bar_aready(bar0, j, RING));
           }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) store8(arow, 128 + cb + 8 * g, acc + 8 * g);
-          if (j == 1) xch5[tw * 128 + t] = part;
-          fence_proxy_async_smem();
-          tc_fence_before_sync();
-          ARRIVE(bar_aready(bar0, j, RING));
         }
       }
 
@@ -562,6 +645,37 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       // both twins arrived on a_ready before this MMA ran: the partial logits are visible
       const float vlogit = cst[T_MISC + 0] + xch5[t] + xch5[128 + t];
       const float vis1 = sigmoid_fast(elu_fast(vlogit)) * mask;
+      if (EA) {
+        tmem_pipe16<4>(tacc + 128, colh, [&](int h, float* v) {
+          const int c0 = colh(h);
+          uint4 pk[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint4 q = *reinterpret_cast<const uint4*>(arow + ((c0 >> 3) + i) * 2048);
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float lo = __uint_as_float(u[k] << 16) + elu_from_log2(v[8 * i + 2 * k]);
+              const float hi = __uint_as_float(u[k] & 0xffff0000u) + elu_from_log2(v[8 * i + 2 * k + 1]);
+              o[k] = pack_bf16x2(lo, hi);
+            }
+            pk[i] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) *reinterpret_cast<uint4*>(arow + ((c0 >> 3) + i) * 2048) = pk[i];
+          if (h & 1) {
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            ARRIVE(bar_aready(bar0, h >> 1, RING));
+          }
+          if (ST && !(a.ablate & 2)) {  // the spill goes out after the arrival (see the non-pipelined branch)
+            uint8_t* xo = reinterpret_cast<uint8_t*>(a.X) + tile_image_off((long long)it * ROWS + t, c0 >> 3, 16);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) *reinterpret_cast<uint4*>(xo + i * 2048) = pk[i];
+          }
+        });
+      } else {
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
         const int cb = 32 * (2 * j + tw);
@@ -603,6 +717,8 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
         }
       }
 
+      }
+
       TS();  // 14: F6 epilogue done
       if (it + (int)gridDim.x < n_iter) fetch_point(it + (int)gridDim.x);  // next iteration's point
       // ---- F7: vis2 = sigmoid(vis_fc2.2 . ELU(vis1 (vis_fc2.0 x) + b)) * mask ----
@@ -611,15 +727,24 @@ __global__ void __launch_bounds__(NT * 256 + 64, NT == 1 ? 2 : 1)
       tc_fence_after_sync();
       {
         float part = 0.f;
-#pragma unroll 1
-        for (int j = 0; j < 2; ++j) {
-          const int cb = 32 * (2 * j + tw);
-          float acc[32];
-          tmem_ld32(tacc + cb, acc);
-          tmem_wait_ld();
+        if (EA) {
+          tmem_pipe16<4>(tacc, colh, [&](int h, float* v) {
+            const int c0 = colh(h);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            part = fmaf(elu_log2(fmaf(acc[i], vis1, cst[T_B7 + cb + i])), cst[T_W8 + cb + i], part);
+            for (int i = 0; i < 16; ++i)
+              part = fmaf(elu_log2(fmaf(v[i], vis1, cst[T_B7 + c0 + i])), cst[T_W8 + c0 + i], part);
+          });
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < 2; ++j) {
+            const int cb = 32 * (2 * j + tw);
+            float acc[32];
+            tmem_ld32(tacc + cb, acc);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              part = fmaf(elu_log2(fmaf(acc[i], vis1, cst[T_B7 + cb + i])), cst[T_W8 + cb + i], part);
+          }
         }
         xch7[tw * 128 + t] = part;
       }
