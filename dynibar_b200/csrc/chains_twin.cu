@@ -158,26 +158,24 @@ __global__ void __launch_bounds__(320, 2) rgbhead_twin_kernel(const __grid_const
       t_wait(c.bar0, acc_cnt);  // rgb_fc.0, per-view part (weights x log2 e): accumulator on the exp2 scale
       // the MMA has consumed columns [0,144): prefetch the next iteration's x block behind it
       if (tid == 0 && it + (int)gridDim.x < n_iter) issue_x(it + (int)gridDim.x);
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        const int cb = c0 + 32 * half;
-        float acc[32];
-        tmem_ld32(tacc + cb, acc);
-        if (half == 1) {
+      // read-out pipelined in 16-column halves; the GW values of half h + 2 are requested as soon as half h has
+      // consumed its own (g[0..3] serve the even halves, g[4..7] the odd ones)
+      tmem_pipe16<4>(tacc, [&](int h) { return c0 + 16 * h; }, [&](int h, float* v) {
+        const int gb = (h & 1) * 4;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = __ldg(reinterpret_cast<const float4*>(gw + (8 + i) * 2048));
+        for (int i = 0; i < 4; ++i) {
+          v[4 * i] = elu_log2(fmaf(g[gb + i].x, kLog2e, v[4 * i]));
+          v[4 * i + 1] = elu_log2(fmaf(g[gb + i].y, kLog2e, v[4 * i + 1]));
+          v[4 * i + 2] = elu_log2(fmaf(g[gb + i].z, kLog2e, v[4 * i + 2]));
+          v[4 * i + 3] = elu_log2(fmaf(g[gb + i].w, kLog2e, v[4 * i + 3]));
         }
-        tmem_wait_ld();
+        if (h < 2) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[4 * i] = elu_log2(fmaf(g[i].x, kLog2e, acc[4 * i]));
-          acc[4 * i + 1] = elu_log2(fmaf(g[i].y, kLog2e, acc[4 * i + 1]));
-          acc[4 * i + 2] = elu_log2(fmaf(g[i].z, kLog2e, acc[4 * i + 2]));
-          acc[4 * i + 3] = elu_log2(fmaf(g[i].w, kLog2e, acc[4 * i + 3]));
+          for (int i = 0; i < 4; ++i) g[gb + i] = __ldg(reinterpret_cast<const float4*>(gw + (8 + 4 * h + i) * 2048));
         }
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) store8(arow, 144 + cb + 8 * gg, acc + 8 * gg);
-      }
+        store8(arow, 144 + c0 + 16 * h, v);
+        store8(arow, 144 + c0 + 16 * h + 8, v + 8);
+      });
       t_ready(c.bar0);
       // masked-softmax inputs of this row (twin 0 blends): loaded before the wait
       float mk = 0.f, c3[3] = {0.f, 0.f, 0.f};
@@ -219,32 +217,37 @@ __global__ void __launch_bounds__(320, 2) rgbhead_twin_kernel(const __grid_const
   twin_teardown(c);
 }
 
-// 32 accumulator columns [col0, col0+32) -> ELU on the exp2 scale -> bf16 operand columns [dst0, dst0+32)
-__device__ __forceinline__ void t_elu_log2_32(uint8_t* arow, uint32_t tacc, int col0, int dst0) {
-  float acc[32];
-  tmem_ld32(tacc + col0, acc);
-  tmem_wait_ld();
+// NB blocks of 32 accumulator columns [col0 + 32 b, ..) -> ELU on the exp2 scale -> bf16 operand columns
+// [dst0 + 32 b, ..); the TMEM read-out is software-pipelined in 16-column halves (fused_engine.cuh: tmem_pipe16)
+template <int NB>
+__device__ __forceinline__ void t_elu_log2_blocks(uint8_t* arow, uint32_t tacc, int col0, int dst0) {
+  tmem_pipe16<2 * NB>(tacc, [&](int h) { return col0 + 16 * h; }, [&](int h, float* v) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = elu_log2(acc[i]);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) store8(arow, dst0 + 8 * g, acc + 8 * g);
+    for (int i = 0; i < 16; ++i) v[i] = elu_log2(v[i]);
+    store8(arow, dst0 + 16 * h, v);
+    store8(arow, dst0 + 16 * h + 8, v + 8);
+  });
 }
-// 32 accumulator columns -> bf16 tile image rows (16 k-groups), zeros for rows past the end
-__device__ __forceinline__ void t_store_image_32(uint32_t tacc, int col0, void* img, long long row, int kgroup0,
-                                                 bool valid) {
-  float acc[32];
-  tmem_ld32(tacc + col0, acc);
-  tmem_wait_ld();
-  if (!valid) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-  }
+__device__ __forceinline__ void t_elu_log2_32(uint8_t* arow, uint32_t tacc, int col0, int dst0) {
+  t_elu_log2_blocks<1>(arow, tacc, col0, dst0);
+}
+// NB blocks of 32 accumulator columns -> bf16 tile image rows (16 k-groups: 4 per block starting at kgroup0),
+// zeros for rows past the end
+template <int NB>
+__device__ __forceinline__ void t_store_image_blocks(uint32_t tacc, int col0, void* img, long long row, int kgroup0,
+                                                     bool valid) {
   uint8_t* o = reinterpret_cast<uint8_t*>(img) + tile_image_off(row, kgroup0, 16);
+  tmem_pipe16<2 * NB>(tacc, [&](int h) { return col0 + 16 * h; }, [&](int h, float* v) {
+    if (!valid) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<uint4*>(o + i * 2048) =
-        make_uint4(pack_bf16x2(acc[8 * i], acc[8 * i + 1]), pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]),
-                   pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]), pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7]));
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      *reinterpret_cast<uint4*>(o + (2 * h + i) * 2048) =
+          make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                     pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  });
 }
 
 // ---------------------------------------------------------------------------
@@ -287,8 +290,7 @@ __global__ void __launch_bounds__(320, 2) point1_twin_kernel(const __grid_consta
       mbar_wait(gbar, g_cnt & 1); ++g_cnt;
       t_ready(c.bar0);
       t_wait(c.bar0, acc_cnt);  // geometry_fc.0 (bias folded, exp2 scale): this twin's 128 of 256 columns
-#pragma unroll 1
-      for (int b = 0; b < 4; ++b) t_elu_log2_32(arow, tacc, 128 * tw + 32 * b, 128 * tw + 32 * b);
+      t_elu_log2_blocks<4>(arow, tacc, 128 * tw, 128 * tw);
       t_ready(c.bar0);
       t_wait(c.bar0, acc_cnt);  // geometry_fc.2 (+ sinusoid for the dynamic net) -> g2: this twin's 64 columns
       {
@@ -324,16 +326,12 @@ __global__ void __launch_bounds__(320, 2) point1_twin_kernel(const __grid_consta
       }
       t_ready(c.bar0);
       t_wait(c.bar0, acc_cnt);  // [Wq ; Wk] (N = 256, no bias): twin 0 stores Q, twin 1 stores K (bf16 tile images)
-#pragma unroll 1
-      for (int b = 0; b < 4; ++b)
-        t_store_image_32(tacc, 128 * tw + 32 * b, tw == 0 ? (void*)a.Q : (void*)a.K, row, 4 * b, valid);
+      t_store_image_blocks<4>(tacc, 128 * tw, tw == 0 ? (void*)a.Q : (void*)a.K, row, 0, valid);
       tc_fence_before_sync();
       mbar_arrive(bar_aready(c.bar0, 0, kTRing));  // operand unchanged; the accumulators are free again
       t_wait(c.bar0, acc_cnt);                     // Wv
       if (tid == 0 && it + (int)gridDim.x < n_iter) issue_g(it + (int)gridDim.x);  // the operand tile is free
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half)
-        t_store_image_32(tacc, 64 * tw + 32 * half, a.V, row, 8 * tw + 4 * half, valid);
+      t_store_image_blocks<2>(tacc, 64 * tw, a.V, row, 8 * tw, valid);
       tc_fence_before_sync();
     }
   }
@@ -471,12 +469,10 @@ __global__ void __launch_bounds__(320, 2) point2_twin_kernel(const __grid_consta
         }
         t_ready(c.bar0);
         t_wait(c.bar0, acc_cnt);  // ref_pts_fc.0 (K = 176, bias folded, exp2 scale): this twin's 128 of 256 columns
-#pragma unroll 1
-        for (int b = 0; b < 4; ++b) t_elu_log2_32(arow, tacc, 128 * tw + 32 * b, 128 * tw + 32 * b);
+        t_elu_log2_blocks<4>(arow, tacc, 128 * tw, 128 * tw);
         t_ready(c.bar0);
         t_wait(c.bar0, acc_cnt);  // ref_pts_fc.2 (K = 256 + bias step) -> g4 on the exp2 scale: 64 columns
-        t_elu_log2_32(arow, tacc, c0, c0);
-        t_elu_log2_32(arow, tacc, c0 + 32, c0 + 32);
+        t_elu_log2_blocks<2>(arow, tacc, c0, c0);
         if (tw == 1) {
           // append PE(dir) (27) at columns 128..154, the bias ones of the next two rounds at 155, 156
           const long long ray = valid ? row / a.S : 0;
@@ -510,8 +506,7 @@ __global__ void __launch_bounds__(320, 2) point2_twin_kernel(const __grid_consta
         x_sig[tw * 128 + r] = part;
       }
       if (DYNAMIC) {
-        t_elu_log2_32(arow, tacc, 128 + c0, c0);        // ELU(rgb_fc.0) -> operand columns [0,128)
-        t_elu_log2_32(arow, tacc, 128 + c0 + 32, c0 + 32);
+        t_elu_log2_blocks<2>(arow, tacc, 128 + c0, c0);  // ELU(rgb_fc.0) -> operand columns [0,128)
         t_ready(c.bar0);
         t_wait(c.bar0, acc_cnt);  // rgb_fc.2 (64, bias folded, exp2 scale) -> rgb_fc.4 (3) as dot products: 32 columns
         if (tid == 0 && it + (int)gridDim.x < n_iter) issue_o(it + (int)gridDim.x);

@@ -44,6 +44,31 @@ __device__ __forceinline__ float sigmoid_fast(float x) {
   return __frcp_rn(1.f + ex2f(-x * 1.4426950408889634f));
 }
 
+// tcgen05.wait::ld that carries a data dependency on the 16 destination registers of the load it waits for (so no
+// use of them can be scheduled above it)
+__device__ __forceinline__ void tmem_wait_ld_dep16(float* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
+
+// Software-pipelined accumulator read-out: NH half-blocks of 16 TMEM columns; the load of half h + 1 is in flight
+// while fn(h, values) processes half h (TMEM reads run at 64 B/clk: a 32-column load of one warp occupies the port
+// for 64 cycles, and eight row warps per CTA queue on it).  colf(h) = TMEM column of half h.
+template <int NH, class ColFn, class Fn>
+__device__ __forceinline__ void tmem_pipe16(uint32_t tacc, ColFn colf, Fn fn) {
+  float buf[2][16];
+  tmem_ld16(tacc + colf(0), buf[0]);
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    tmem_wait_ld_dep16(buf[h & 1]);
+    if (h + 1 < NH) tmem_ld16(tacc + colf(h + 1), buf[(h + 1) & 1]);
+    fn(h, buf[h & 1]);
+  }
+}
+
 // 8 consecutive columns [c0, c0+8) of this thread's row -> one 16-byte store
 __device__ __forceinline__ void store8(uint8_t* arow, int c0, const float* v) {
   uint4 q;
