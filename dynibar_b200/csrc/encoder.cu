@@ -278,11 +278,6 @@ __global__ void enc_relu_mask_kernel(float* __restrict__ g, const float* __restr
   if (i < n && !(y[i] > 0.f)) g[i] = 0.f;
 }
 
-__global__ void enc_add_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] += b[i];
-}
-
 // InstanceNorm2d backward, one block per (image, channel) plane: xh = (x - mean) rstd,
 // dx = rstd gamma (dy - mean(dy) - xh mean(dy xh)); dgamma += sum dy xh, dbeta += sum dy.  dx may alias dy.
 __global__ void __launch_bounds__(256) enc_in_bwd_kernel(const float* __restrict__ x, const float* dy,
