@@ -4,7 +4,7 @@
  * this path is the Python call surface of ibrnet/render_ray.py,
  * ibrnet/projection.py and ibrnet/mlp_network.py.  Each entry point below
  * names the reference function (file:line under /root/reference) it replaces;
- * `dynibar_b200/*.py` binds them with ctypes behind the reference's own
+ * the Python modules under dynibar_b200/ bind them with ctypes behind the reference's own
  * function / class names.
  *
  * Conventions
